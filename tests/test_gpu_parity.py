@@ -1,0 +1,189 @@
+"""GPU parity tests (run on a B200 with -m gpu).  Everything goes through the C ABI (libtidalwave_b200.so).
+
+Bar (BASELINE.json north_star): per-pixel flow within 1e-2 px max-abs and 1e-3 px RMS of the reference's CPU Farneback
+path, classification (status + vector positions) identical.  Per-stage tensors are compared with the oracle to localise
+failures; stage tolerances are tight because both sides follow SURVEY App. A's operation order."""
+import numpy as np
+import pytest
+
+from conftest import OPTS, golden_pair
+from oracle.oracle import FlowParam, sample_numpy
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAX, TOL_RMS = 1e-2, 1e-3
+
+
+@pytest.fixture(scope="module")
+def of(tw):
+    o = tw.OpticalFlow(0, 1920, 1080, 4)
+    yield o
+    o.close()
+
+
+def _check_flow(fx, fy, ref, what):
+    d = np.maximum(np.abs(fx - ref[..., 0]), np.abs(fy - ref[..., 1]))
+    rms = float(np.sqrt(((fx - ref[..., 0]) ** 2 + (fy - ref[..., 1]) ** 2).mean() / 2))
+    assert d.max() <= TOL_MAX and rms <= TOL_RMS, f"{what}: max {d.max():.3e} rms {rms:.3e}"
+    return float(d.max())
+
+
+def _vec_pos(resp):
+    return [(v["x"], v["y"]) for v in resp["vector"]]
+
+
+def test_reference_golden_cases(of, golden):
+    """/root/reference/test/index.coffee:12-96 replayed through tw_compare."""
+    thr, span = golden["options"]["threshold"], golden["options"]["span"]
+    for case in golden["cases"]:
+        a, b = golden["imgs"][case["expect"]], golden["imgs"][case["target"]]
+        resp = of.calculate(a, b, threshold=thr, span=span)
+        assert resp["status"] == case["status"]
+        assert (resp["height"], resp["width"], resp["span"], resp["threshold"]) == (case["height"], case["width"], span, thr)
+        assert _vec_pos(resp) == [(g["x"], g["y"]) for g in case["vector"]]
+        for v, g in zip(resp["vector"], case["vector"]):
+            assert abs(v["dx"] - g["dx"]) < 1e-3 and abs(v["dy"] - g["dy"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["s1", "s2r2", "S256", "T256", "Sdef"])
+@pytest.mark.parametrize("opt", list(OPTS))
+def test_flow_vs_oracle_and_cv2(of, tw, oracle, golden, name, opt):
+    a, b = golden_pair(golden, tw, name)
+    p = tw.OpticalFlowParameter(**OPTS[opt])
+    rc, fx, fy, sec = of.calculateInternal(a, b, p)
+    assert rc == 0, of.last_error()
+    assert sec > 0
+    ref = oracle.farneback(a, b, FlowParam(**OPTS[opt]))
+    _check_flow(fx, fy, ref, f"{name}/{opt} vs oracle")
+    key = f"{name}__{opt}"
+    if key in golden["flows"]:
+        _check_flow(fx, fy, golden["flows"][key], f"{name}/{opt} vs cv2 golden")
+    # classification identity
+    resp = of.calculate(a, b, p)
+    status, vec = oracle.sample(ref)
+    assert resp["status"] == status
+    assert _vec_pos(resp) == [(v[0], v[1]) for v in vec]
+    flow = np.stack([fx, fy], -1)
+    assert [(v["x"], v["y"], v["dx"], v["dy"]) for v in resp["vector"]] == sample_numpy(flow)[1]
+
+
+@pytest.mark.parametrize("opt", ["default", "cfg4"])
+def test_per_stage_parity(tw, oracle, golden, opt):
+    """Stage-by-stage against the oracle's dump: level images, polynomial expansion, update-matrices input of the last
+    iteration, per-scale flow."""
+    a, b = golden_pair(golden, tw, "Sdef")
+    of = tw.OpticalFlow(0, 320, 200, 1)
+    of.debug_keep_levels(True)
+    p = tw.OpticalFlowParameter(**OPTS[opt])
+    rc, fx, fy, _ = of.calculateInternal(a, b, p)
+    assert rc == 0
+    dump = {}
+    oracle.farneback(a, b, FlowParam(**OPTS[opt]), dump=dump)
+    nscales = 1 + max(k[1] for k in dump)
+    iters = p.pyrIterations
+    for s in range(nscales):
+        for nm in ("I0", "I1"):
+            got = of.debug_read(nm, s)[0]
+            np.testing.assert_array_equal(got, dump[(nm, s, 0)], err_msg=f"{nm} scale {s}")
+        for nm in ("R0", "R1"):
+            got = of.debug_read(nm, s).transpose(1, 2, 0)
+            np.testing.assert_array_equal(got, dump[(nm, s, 0)], err_msg=f"{nm} scale {s}")
+        if s == 0:
+            # coarsest scale: the whole chain is deterministic given identical inputs
+            got = of.debug_read("M", s).transpose(1, 2, 0)
+            want = dump[("M", s, iters - 1)]
+            assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+        got = of.debug_read("flow", s).transpose(1, 2, 0)
+        want = dump[("flow", s, iters - 1)]
+        assert np.abs(got - want).max() <= TOL_MAX, f"flow scale {s}: {np.abs(got - want).max()}"
+    of.close()
+
+
+def test_batch_equals_single(of, tw):
+    pairs = [tw.synth.make_pair("S", 320, 200, 20 + i, defect=(i % 2 == 0)) for i in range(4)]
+    single = [of.calculate(a, b) for a, b in pairs]
+    batch = of.calculate_batch(pairs)
+    for s, bt in zip(single, batch):
+        assert s["status"] == bt["status"] and s["vector"] == bt["vector"]
+    assert any(r["status"] == "SUSPICIOUS" for r in batch) and any(len(r["vector"]) > 0 for r in batch)
+
+
+def test_known_shift_recovered(of, tw):
+    """Synthetic texture with a known translation: the mean flow must recover (-0.37, +0.61)."""
+    a, b = tw.synth.make_pair("T", 640, 360, 1)
+    rc, fx, fy, _ = of.calculateInternal(a, b)
+    assert rc == 0
+    assert abs(float(fx[40:-40, 40:-40].mean()) + 0.37) < 0.05 and abs(float(fy[40:-40, 40:-40].mean()) - 0.61) < 0.05
+    assert of.calculate(a, b)["status"] == "OK"
+
+
+def test_identical_images_ok(of, golden):
+    a = golden["imgs"]["s1_expected"]
+    r = of.calculate(a, a.copy())
+    assert r["status"] == "OK" and r["vector"] == [] and (r["height"], r["width"]) == (279, 280)
+
+
+def test_error_codes(of, tw):
+    """src/opticalflow.cpp:26-61 error behaviour at the C ABI."""
+    a = np.zeros((100, 120), np.uint8)
+    r = of.calculate(a, np.zeros((100, 126), np.uint8))
+    assert r["status"] == "ERROR" and r["code"] == 3 and r["reason"] == "Don't match image size"
+    r = of.calculate(a, np.zeros((106, 120), np.uint8))
+    assert r["code"] == 3
+    r = of.calculate(None, a)
+    assert r["status"] == "ERROR" and r["code"] == 2 and r["reason"].startswith("Can't open")
+    r = of.calculate(a, None)
+    assert r["code"] == 2
+    for bad in (dict(pyrScale=1.0), dict(flags=4), dict(flags=260), dict(polyN=0), dict(winSize=1), dict(pyrLevels=-1)):
+        r = of.calculate(a, a, tw.OpticalFlowParameter(**bad))
+        assert r["status"] == "ERROR" and r["code"] == 1, bad
+    # the context survives errors
+    assert of.calculate(a, a)["status"] == "OK"
+
+
+def test_vector_cap_truncates(of, golden):
+    a, b = golden["imgs"]["s2_expected"], golden["imgs"]["s2_revision2"]
+    r = of.calculate(a, b, cap=5)
+    assert r["n_vectors"] == 24 and len(r["vector"]) == 5 and r["vector"][0]["x"] == 80
+
+
+def test_threshold_and_span_options(of, oracle, golden):
+    a, b = golden["imgs"]["s2_expected"], golden["imgs"]["s2_revision2"]
+    ref = oracle.farneback(a, b, FlowParam())
+    for thr, span in ((2.0, 7), (0.5, 1), (50.0, 10), (5.0, 3)):
+        r = of.calculate(a, b, threshold=thr, span=span)
+        status, vec = oracle.sample(ref, span, thr)
+        assert r["status"] == status and _vec_pos(r) == [(v[0], v[1]) for v in vec], (thr, span)
+
+
+def test_pool_dispatch(tw, golden):
+    """Manager/Consumer semantics (src/manager.cpp:40-98): results independent of worker count / order; Report counters."""
+    a, b = golden["imgs"]["s2_expected"], golden["imgs"]["s2_revision2"]
+    s1 = golden["imgs"]["s1_expected"]
+    pairs = [(a, b), (s1, s1), (a, a), (a, b), (a, np.zeros((200, 200), np.uint8)), (s1, s1), (a, b)]
+    results = {}
+    for devices, batch in (([0], 1), ([0, 0], 2), ([0, 0, 0], 4)):
+        pool = tw.Pool(devices, batch=batch, max_w=280, max_h=279)
+        ids = [pool.request(x, y) for x, y in pairs]
+        out = [pool.wait(i) for i in ids]
+        rep = pool.report()
+        pool.stop()
+        pool.close()
+        assert rep == {"request": 7, "data": 6, "error": 1}
+        results[(len(devices), batch)] = [(r["status"], r.get("vector")) for r in out]
+    vals = list(results.values())
+    assert vals[0] == vals[1] == vals[2]
+    assert [s for s, _ in vals[0]] == ["SUSPICIOUS", "OK", "OK", "SUSPICIOUS", "ERROR", "OK", "SUSPICIOUS"]
+    assert len(vals[0][0][1]) == 24
+
+
+def test_pool_stop_drops_pending(tw, golden):
+    s1 = golden["imgs"]["s1_expected"]
+    pool = tw.Pool([0], batch=1, max_w=280, max_h=279)
+    ids = [pool.request(s1, s1) for _ in range(50)]
+    pool.stop()
+    got = [pool.wait(i) for i in ids]
+    rep = pool.report()
+    assert rep["request"] == 50 and rep["data"] + sum(g is None for g in got) == 50
+    assert pool.request(s1, s1) < 0
+    pool.close()

@@ -1,0 +1,799 @@
+// tw_context.cu -- host side of the C ABI: context, per-shape plan (pyramid schedule + tables), the launch
+// sequence, result fetch, measurement hooks.  Mirrors OpticalFlow::calculate / calculateInternal
+// (/root/reference/src/opticalflow.cpp:20-119) and the sampling of Consumer::run (src/consumer.cpp:59-88).
+#include "../../include/tidalwave_b200.h"
+#include "tw_kernels.cuh"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tw;
+
+namespace {
+
+enum Family { F_LEVEL = 0, F_POLY, F_FIRST, F_GITER, F_GLAST, F_BVSUM, F_BITER, F_BLAST, F_SAMPLE, F_COUNT };
+const char *kFamilyNames[F_COUNT] = {"level_image", "polyexp", "first_update", "gauss_iter", "gauss_last",
+                                     "box_vsum", "box_iter", "box_last", "sample"};
+
+struct Scale {
+    int k, ksize;
+    double sigma;
+    LevelDims d;
+    // device tables
+    int *img_xi = nullptr, *img_yi = nullptr, *up_xi = nullptr, *up_yi = nullptr;
+    float *img_xf = nullptr, *img_yf = nullptr, *up_xf = nullptr, *up_yf = nullptr;
+    float *taps = nullptr;
+    int tile_w = 32, tile_h = 8, smem_w = 0, smem_h = 0, identity = 0;
+    // buffers (alias the shared work buffers unless keep_levels)
+    float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr, *flow = nullptr;
+};
+
+struct Plan {
+    bool valid = false;
+    int W = 0, H = 0, batch = 0, keep = 0;
+    tw_flow_param p{};
+    std::vector<Scale> scales; // coarse -> fine
+    PolyTables poly{};
+    WinTaps win{};
+    std::vector<void *> allocs;
+    uint8_t *src = nullptr; // [B][2][H][spitch]
+    int spitch = 0;
+    double *V = nullptr; // box only
+    float *last_M = nullptr;
+};
+
+} // namespace
+
+struct tw_ctx {
+    int device = 0;
+    int max_w = 0, max_h = 0, max_batch = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
+    Plan plan;
+    int keep_levels = 0;
+    // results
+    int *d_counts = nullptr;
+    int *h_counts = nullptr; // pinned
+    void *d_vectors = nullptr;
+    int dev_cap = 0;
+    int last_n = 0, last_w = 0, last_h = 0;
+    bool ran = false;
+    // profiling
+    bool profiling = false;
+    struct Rec { int fam; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> ev_pool;
+    float fam_ms[F_COUNT] = {0};
+    int fam_launches[F_COUNT] = {0};
+    double fam_bytes[F_COUNT] = {0};
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int cv_round(double v) { return (int)nearbyint(v); }
+
+bool set_err(tw_ctx *c, const char *what, cudaError_t e)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    c->err = buf;
+    return false;
+}
+
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) { set_err(ctx, #call, e_); return false; } \
+    } while (0)
+
+void free_plan(tw_ctx *ctx)
+{
+    for (void *p : ctx->plan.allocs) cudaFree(p);
+    ctx->plan = Plan();
+}
+
+template <typename T>
+bool dev_alloc(tw_ctx *ctx, T **out, size_t count)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return set_err(ctx, "cudaMalloc", e);
+    ctx->plan.allocs.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return true;
+}
+
+template <typename T>
+bool dev_upload(tw_ctx *ctx, T **out, const std::vector<T> &v)
+{
+    if (!dev_alloc(ctx, out, v.size())) return false;
+    CK(cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // v is a temporary
+    return true;
+}
+
+// per-axis bilinear coefficients (double expression, one cast).
+void resize_coeffs(int N, int n, std::vector<int> &idx, std::vector<float> &frac)
+{
+    idx.resize(n); frac.resize(n);
+    double s = 1.0 / (n / (double)N);
+    for (int d = 0; d < n; d++) {
+        float f = (float)((d + 0.5) * s - 0.5);
+        int i = (int)floorf(f);
+        f = f - (float)i;
+        if (i < 0) { f = 0; i = 0; }
+        if (i >= N - 1) { f = 0; i = N - 1; }
+        idx[d] = i; frac[d] = f;
+    }
+}
+
+// cv::getGaussianKernel(ksize, sigma, CV_32F).
+std::vector<float> gauss_taps(int ksize, double sigma)
+{
+    std::vector<float> k(ksize);
+    if (sigma <= 0 && ksize == 3) { k[0] = 0.25f; k[1] = 0.5f; k[2] = 0.25f; return k; }
+    double sx = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    double scale2x = -0.5 / (sx * sx), sum = 0;
+    std::vector<double> t(ksize);
+    for (int i = 0; i < ksize; i++) {
+        double x = i - (ksize - 1) * 0.5;
+        t[i] = std::exp(scale2x * x * x);
+        sum += t[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i < ksize; i++) k[i] = (float)(t[i] * sum);
+    return k;
+}
+
+void invert6(double A[6][6], double inv[6][6])
+{
+    double a[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { a[i][j] = A[i][j]; a[i][j + 6] = (i == j); }
+    for (int c = 0; c < 6; c++) {
+        int p = c;
+        for (int r = c + 1; r < 6; r++) if (std::fabs(a[r][c]) > std::fabs(a[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 12; j++) std::swap(a[c][j], a[p][j]);
+        double d = a[c][c];
+        for (int j = 0; j < 12; j++) a[c][j] /= d;
+        for (int r = 0; r < 6; r++) if (r != c) {
+            double f = a[r][c];
+            if (f != 0) for (int j = 0; j < 12; j++) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) inv[i][j] = a[i][j + 6];
+}
+
+// SURVEY App. A.3 tables (FarnebackPrepareGaussian).
+void poly_tables(int n, double sigma, PolyTables &t)
+{
+    if (sigma < FLT_EPSILON) sigma = n * 0.3;
+    std::vector<float> gb(2 * n + 1), xgb(2 * n + 1), xxgb(2 * n + 1);
+    float *g = gb.data() + n, *xg = xgb.data() + n, *xxg = xxgb.data() + n;
+    double s = 0.;
+    for (int x = -n; x <= n; x++) { g[x] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += g[x]; }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)(g[x] * s);
+        xg[x] = (float)(x * g[x]);
+        xxg[x] = (float)(x * x * g[x]);
+    }
+    double G[6][6] = {{0}}, inv[6][6];
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            float wgt = g[y] * g[x], fx = (float)x, fy = (float)y;
+            G[0][0] += wgt;
+            G[1][1] += wgt * fx * fx;
+            G[3][3] += wgt * fx * fx * fx * fx;
+            G[5][5] += wgt * fx * fx * fy * fy;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    invert6(G, inv);
+    t.n = n;
+    t.ig11 = inv[1][1]; t.ig03 = inv[0][3]; t.ig33 = inv[3][3]; t.ig55 = inv[5][5];
+    for (int x = 0; x <= n; x++) { t.g[x] = g[x]; t.xg[x] = xg[x]; t.xxg[x] = xxg[x]; }
+}
+
+// SURVEY App. A.5 window taps.
+void window_taps(int winSize, WinTaps &t)
+{
+    int m = winSize / 2;
+    double sigma = m * 0.3, s = 1.;
+    t.m = m;
+    t.k[0] = 1.f;
+    for (int i = 1; i <= m; i++) {
+        float v = (float)std::exp(-i * i / (2 * sigma * sigma));
+        t.k[i] = v;
+        s += v * 2;
+    }
+    s = 1. / s;
+    for (int i = 0; i <= m; i++) t.k[i] = (float)(t.k[i] * s);
+}
+
+int validate_param(const tw_flow_param *p)
+{
+    if (!p) return TW_BAD_PARAMETER;
+    if (!(p->pyrScale > 0 && p->pyrScale < 1)) return TW_BAD_PARAMETER;
+    if (p->pyrLevels < 0 || p->pyrLevels > 14) return TW_BAD_PARAMETER;
+    if (p->polyN != 5 && p->polyN != 7) return TW_BAD_PARAMETER;
+    if (p->flags != 0 && p->flags != 256) return TW_BAD_PARAMETER;
+    if (p->winSize < 2 || p->winSize / 2 > kMaxWinRadius) return TW_BAD_PARAMETER;
+    if (p->pyrIterations < 0 || p->pyrIterations > 100) return TW_BAD_PARAMETER;
+    if (!(p->polySigma >= 0)) return TW_BAD_PARAMETER;
+    return TW_OK;
+}
+
+bool same_param(const tw_flow_param &a, const tw_flow_param &b)
+{
+    return a.pyrScale == b.pyrScale && a.pyrLevels == b.pyrLevels && a.winSize == b.winSize &&
+           a.pyrIterations == b.pyrIterations && a.polyN == b.polyN && a.polySigma == b.polySigma && a.flags == b.flags;
+}
+
+bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
+{
+    Plan &pl = ctx->plan;
+    if (pl.valid && pl.W == W && pl.H == H && pl.batch == ctx->max_batch && pl.keep == ctx->keep_levels && same_param(pl.p, p))
+        return true;
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_plan(ctx);
+    pl.W = W; pl.H = H; pl.p = p; pl.batch = ctx->max_batch; pl.keep = ctx->keep_levels;
+    const int B = pl.batch;
+
+    // A.1 schedule
+    int k; double scale = 1.0;
+    for (k = 0; k < p.pyrLevels; k++) {
+        scale *= p.pyrScale;
+        if (W * scale < 32 || H * scale < 32) break;
+    }
+    const int L = k;
+    for (k = L; k >= 0; k--) {
+        Scale s;
+        scale = 1.0;
+        for (int i = 0; i < k; i++) scale *= p.pyrScale;
+        s.k = k;
+        s.sigma = (1. / scale - 1) * 0.5;
+        s.ksize = std::max(cv_round(s.sigma * 5) | 1, 3);
+        s.d.w = cv_round(W * scale); s.d.h = cv_round(H * scale);
+        s.d.pitch = (s.d.w + 31) & ~31;
+        s.d.plane = (size_t)s.d.h * s.d.pitch;
+        if (s.ksize > 1023 || s.d.w < 1 || s.d.h < 1) { ctx->err = "unsupported pyramid geometry"; return false; }
+        pl.scales.push_back(s);
+    }
+    poly_tables(p.polyN, p.polySigma, pl.poly);
+    window_taps(p.winSize, pl.win);
+
+    pl.spitch = (W + 15) & ~15;
+    if (!dev_alloc(ctx, &pl.src, (size_t)B * 2 * H * pl.spitch)) return false;
+
+    // tables + tile geometry
+    for (size_t si = 0; si < pl.scales.size(); si++) {
+        Scale &s = pl.scales[si];
+        std::vector<int> xi, yi; std::vector<float> xf, yf;
+        resize_coeffs(W, s.d.w, xi, xf);
+        resize_coeffs(H, s.d.h, yi, yf);
+        s.identity = (s.d.w == W && s.d.h == H);
+        const int c = s.ksize / 2;
+        // choose an output tile whose source tile fits comfortably in shared memory
+        int tw_ = 32, th_ = 8;
+        for (;;) {
+            int sw = 0, sh = 0;
+            for (int d0 = 0; d0 < s.d.w; d0 += tw_) {
+                int d1 = std::min(d0 + tw_, s.d.w) - 1;
+                sw = std::max(sw, (xi[d1] + 1 + c) - (xi[d0] - c) + 1);
+            }
+            for (int e0 = 0; e0 < s.d.h; e0 += th_) {
+                int e1 = std::min(e0 + th_, s.d.h) - 1;
+                sh = std::max(sh, (yi[e1] + 1 + c) - (yi[e0] - c) + 1);
+            }
+            sw = std::min(sw, W); sh = std::min(sh, H);
+            size_t bytes = (size_t)sh * ((sw + 3) & ~3) + 16 + sizeof(float) * ((size_t)sh * tw_ * 2 + s.ksize);
+            if (bytes <= 96 * 1024 || (tw_ == 1 && th_ == 1)) { s.smem_w = sw; s.smem_h = sh; break; }
+            if (tw_ >= th_ * 2 && tw_ > 1) tw_ /= 2; else if (th_ > 1) th_ /= 2; else tw_ /= 2;
+        }
+        s.tile_w = tw_; s.tile_h = th_;
+        if (!dev_upload(ctx, &s.img_xi, xi) || !dev_upload(ctx, &s.img_xf, xf) || !dev_upload(ctx, &s.img_yi, yi) ||
+            !dev_upload(ctx, &s.img_yf, yf))
+            return false;
+        if (!dev_upload(ctx, &s.taps, gauss_taps(s.ksize, s.sigma))) return false;
+        if (si > 0) {
+            const Scale &cs = pl.scales[si - 1];
+            resize_coeffs(cs.d.w, s.d.w, xi, xf);
+            resize_coeffs(cs.d.h, s.d.h, yi, yf);
+            if (!dev_upload(ctx, &s.up_xi, xi) || !dev_upload(ctx, &s.up_xf, xf) || !dev_upload(ctx, &s.up_yi, yi) ||
+                !dev_upload(ctx, &s.up_yf, yf))
+                return false;
+        }
+        if (!dev_alloc(ctx, &s.flow, (size_t)B * 2 * s.d.plane)) return false;
+    }
+    // work buffers: shared across scales (sized for the finest) unless keep_levels
+    const Scale &fine = pl.scales.back();
+    float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr;
+    if (!ctx->keep_levels) {
+        if (!dev_alloc(ctx, &I, (size_t)B * 2 * fine.d.plane) || !dev_alloc(ctx, &R, (size_t)B * 10 * fine.d.plane) ||
+            !dev_alloc(ctx, &M0, (size_t)B * 5 * fine.d.plane) || !dev_alloc(ctx, &M1, (size_t)B * 5 * fine.d.plane))
+            return false;
+    }
+    for (Scale &s : pl.scales) {
+        if (ctx->keep_levels) {
+            if (!dev_alloc(ctx, &s.I, (size_t)B * 2 * s.d.plane) || !dev_alloc(ctx, &s.R, (size_t)B * 10 * s.d.plane) ||
+                !dev_alloc(ctx, &s.M0, (size_t)B * 5 * s.d.plane) || !dev_alloc(ctx, &s.M1, (size_t)B * 5 * s.d.plane))
+                return false;
+        } else {
+            s.I = I; s.R = R; s.M0 = M0; s.M1 = M1;
+        }
+    }
+    if (p.flags == 0 && !dev_alloc(ctx, &pl.V, (size_t)B * 5 * fine.d.plane)) return false;
+    pl.valid = true;
+    return true;
+}
+
+cudaEvent_t get_event(tw_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+struct LaunchScope {
+    tw_ctx *ctx; int fam; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(tw_ctx *c, int f, double bytes) : ctx(c), fam(f)
+    {
+        ctx->launches++;
+        if (ctx->profiling) {
+            a = get_event(ctx); b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+            ctx->fam_bytes[fam] += bytes;
+            ctx->fam_launches[fam]++;
+        }
+    }
+    ~LaunchScope()
+    {
+        if (ctx->profiling) { cudaEventRecord(b, ctx->stream); ctx->recs.push_back({fam, a, b}); }
+    }
+};
+
+void drain_profile(tw_ctx *ctx)
+{
+    for (auto &r : ctx->recs) {
+        float ms = 0;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->fam_ms[r.fam] += ms;
+        ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+    }
+    ctx->recs.clear();
+}
+
+#define LAUNCH(fam, bytes, expr)                                          \
+    do {                                                                  \
+        LaunchScope ls_(ctx, fam, bytes);                                 \
+        cudaError_t e_ = (expr);                                          \
+        if (e_ != cudaSuccess) { set_err(ctx, #expr, e_); return false; } \
+    } while (0)
+
+bool ensure_results(tw_ctx *ctx, int cap)
+{
+    if (ctx->d_vectors && ctx->dev_cap >= cap) return true;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_vectors) cudaFree(ctx->d_vectors);
+    ctx->d_vectors = nullptr;
+    CK(cudaMalloc(&ctx->d_vectors, (size_t)ctx->max_batch * cap * sizeof(tw_vector)));
+    ctx->dev_cap = cap;
+    return true;
+}
+
+// The launch sequence for n pairs already resident in plan.src.  SURVEY App. A.1 / A.7.
+bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
+{
+    Plan &pl = ctx->plan;
+    const tw_flow_param &p = pl.p;
+    const int W = pl.W, H = pl.H;
+    const double P0 = (double)W * H;
+    const size_t ns = pl.scales.size();
+    for (size_t si = 0; si < ns; si++) {
+        Scale &s = pl.scales[si];
+        const double Pl = (double)s.d.w * s.d.h;
+        LevelImageArgs la{};
+        la.src = pl.src; la.W = W; la.H = H; la.spitch = pl.spitch; la.dst = s.I; la.d = s.d;
+        la.xi = s.img_xi; la.xf = s.img_xf; la.yi = s.img_yi; la.yf = s.img_yf; la.taps = s.taps; la.ksize = s.ksize;
+        la.nimg = 2 * n; la.tile_w = s.tile_w; la.tile_h = s.tile_h; la.smem_w = s.smem_w; la.smem_h = s.smem_h;
+        la.identity = s.identity;
+        // I planes of a batch are laid out [B][2]: the u8 source is [B][2] too, so image index = blockIdx.z.
+        LAUNCH(F_LEVEL, n * (2 * P0 + 8 * Pl), launch_level_image(ctx->stream, la));
+        LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly));
+
+        FirstUpdateArgs fa{};
+        if (si > 0) {
+            const Scale &cs = pl.scales[si - 1];
+            fa.coarse = cs.flow; fa.cd = cs.d; fa.xi = s.up_xi; fa.xf = s.up_xf; fa.yi = s.up_yi; fa.yf = s.up_yf;
+        }
+        fa.inv_scale = (float)(1. / p.pyrScale);
+        fa.R = s.R; fa.d = s.d; fa.batch = n;
+        fa.M = p.pyrIterations > 0 ? s.M0 : nullptr;
+        fa.flow_out = p.pyrIterations > 0 ? nullptr : s.flow;
+        double cbytes = si > 0 ? 8.0 * pl.scales[si - 1].d.w * pl.scales[si - 1].d.h : 0.0;
+        LAUNCH(F_FIRST, n * (cbytes + 60 * Pl), launch_first_update(ctx->stream, fa));
+
+        float *Min = s.M0, *Mout = s.M1;
+        for (int it = 0; it < p.pyrIterations; it++) {
+            IterArgs ia{};
+            ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
+            ia.last = (it == p.pyrIterations - 1);
+            double bytes = n * (ia.last ? 28 : 80) * Pl;
+            if (p.flags & 256) {
+                LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
+            } else {
+                LAUNCH(F_BVSUM, 0.0, launch_box_vsum(ctx->stream, Min, pl.V, s.d, n, p.winSize / 2));
+                LAUNCH(ia.last ? F_BLAST : F_BITER, bytes, launch_box_iter(ctx->stream, pl.V, ia, p.winSize / 2, p.winSize));
+            }
+            if (!ia.last) std::swap(Min, Mout);
+        }
+        pl.last_M = Min;
+    }
+    if (span > 0) {
+        Scale &f = pl.scales.back();
+        int nsx = (f.d.w + span - 1) / span, nsy = (f.d.h + span - 1) / span;
+        if (!ensure_results(ctx, nsx * nsy)) return false;
+        SampleArgs sa{};
+        sa.flow = f.flow; sa.d = f.d; sa.batch = n; sa.span = span; sa.thr2 = threshold * threshold;
+        sa.counts = ctx->d_counts; sa.vectors = ctx->d_vectors; sa.cap = ctx->dev_cap;
+        LAUNCH(F_SAMPLE, 0.0, launch_sample(ctx->stream, sa));
+    }
+    return true;
+}
+
+void fill_error(tw_result *r, int code, const char *msg)
+{
+    memset(r, 0, sizeof *r);
+    r->code = code;
+    r->status = TW_STATUS_ERROR;
+    snprintf(r->reason, sizeof r->reason, "%s", msg);
+}
+
+} // namespace
+
+extern "C" {
+
+void tw_default_param(tw_flow_param *p)
+{
+    p->pyrScale = 0.5; p->pyrLevels = 3; p->winSize = 30; p->pyrIterations = 3; p->polyN = 7; p->polySigma = 1.5; p->flags = 256;
+}
+
+const char *tw_version(void) { return "tidalwave_b200 0.1 sm_100a"; }
+
+int tw_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, int errlen)
+{
+    auto fail = [&](const std::string &m) -> tw_ctx * {
+        if (err && errlen > 0) snprintf(err, errlen, "%s", m.c_str());
+        return nullptr;
+    };
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("bad device index");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return fail(b);
+    }
+    tw_ctx *ctx = new tw_ctx();
+    ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
+    cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
+    if ((e = cudaMalloc(&ctx->d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess) {
+        std::string m = cudaGetErrorString(e);
+        tw_destroy(ctx);
+        return fail(m);
+    }
+    return ctx;
+}
+
+void tw_destroy(tw_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drain_profile(ctx);
+    free_plan(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->d_vectors) cudaFree(ctx->d_vectors);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_r0) cudaEventDestroy(ctx->ev_r0);
+    if (ctx->ev_r1) cudaEventDestroy(ctx->ev_r1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *tw_last_error(tw_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void *tw_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void tw_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int tw_sync(tw_ctx *ctx)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "sync", e); return TW_CUDA_ERROR; }
+    return TW_OK;
+}
+
+// Upload of n pairs is shared by the batch entry points.  The plan must exist for (w, h): built lazily here
+// with the last parameters (or defaults) and rebuilt by tw_batch_run if the parameters differ.
+static int upload_impl(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h,
+                       int stride, const tw_flow_param *param)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    if (n < 1 || n > ctx->max_batch || w < 1 || h < 1 || stride < w) { ctx->err = "bad batch/size"; return TW_BAD_PARAMETER; }
+    cudaSetDevice(ctx->device);
+    tw_flow_param p;
+    if (param) p = *param; else if (ctx->plan.valid) p = ctx->plan.p; else tw_default_param(&p);
+    if (validate_param(&p) != TW_OK) { ctx->err = "bad optical-flow parameter"; return TW_BAD_PARAMETER; }
+    if (!build_plan(ctx, w, h, p)) return TW_CUDA_ERROR;
+    Plan &pl = ctx->plan;
+    for (int i = 0; i < n; i++) {
+        if (!expect[i] || !target[i]) { ctx->err = "null image"; return TW_BAD_IMAGE_FORMAT; }
+        uint8_t *d = pl.src + (size_t)i * 2 * h * pl.spitch;
+        cudaError_t e = cudaMemcpy2DAsync(d, pl.spitch, expect[i], stride, w, h, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(d + (size_t)h * pl.spitch, pl.spitch, target[i], stride, w, h, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { set_err(ctx, "H2D", e); return TW_CUDA_ERROR; }
+    }
+    return TW_OK;
+}
+
+int tw_batch_upload(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride)
+{
+    return upload_impl(ctx, n, expect, target, w, h, stride, nullptr);
+}
+
+int tw_batch_run(tw_ctx *ctx, int n, int w, int h, const tw_flow_param *param, double threshold, int span)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    if (n < 1 || n > ctx->max_batch) { ctx->err = "bad batch"; return TW_BAD_PARAMETER; }
+    if (validate_param(param) != TW_OK) { ctx->err = "bad optical-flow parameter"; return TW_BAD_PARAMETER; }
+    if (span < 0) { ctx->err = "bad span"; return TW_BAD_PARAMETER; }
+    cudaSetDevice(ctx->device);
+    Plan &pl = ctx->plan;
+    if (!(pl.valid && pl.W == w && pl.H == h && pl.batch == ctx->max_batch && pl.keep == ctx->keep_levels)) {
+        ctx->err = "tw_batch_run: no uploaded images of this size";
+        return TW_BAD_PARAMETER;
+    }
+    if (!same_param(pl.p, *param)) {
+        // parameters changed but the images are already resident: rebuild the plan around a copy of src
+        uint8_t *tmp = nullptr;
+        size_t bytes = (size_t)pl.batch * 2 * h * pl.spitch;
+        cudaError_t e = cudaMalloc(&tmp, bytes);
+        if (e != cudaSuccess) { set_err(ctx, "cudaMalloc", e); return TW_CUDA_ERROR; }
+        cudaMemcpyAsync(tmp, pl.src, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        bool ok = build_plan(ctx, w, h, *param);
+        if (ok) cudaMemcpyAsync(ctx->plan.src, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        if (!ok) return TW_CUDA_ERROR;
+    }
+    cudaEventRecord(ctx->ev_r0, ctx->stream);
+    if (!enqueue(ctx, n, threshold, span)) return TW_CUDA_ERROR;
+    cudaEventRecord(ctx->ev_r1, ctx->stream);
+    ctx->last_n = n; ctx->last_w = w; ctx->last_h = h; ctx->ran = true;
+    return TW_OK;
+}
+
+int tw_batch_fetch(tw_ctx *ctx, int n, tw_vector *out, int cap, tw_result *res)
+{
+    if (!ctx || !res) return TW_BAD_PARAMETER;
+    if (!ctx->ran || n != ctx->last_n) { ctx->err = "tw_batch_fetch: nothing to fetch"; return TW_BAD_PARAMETER; }
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_err(ctx, "fetch", e);
+        for (int i = 0; i < n; i++) fill_error(&res[i], TW_CUDA_ERROR, ctx->err.c_str());
+        return TW_CUDA_ERROR;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_r0, ctx->ev_r1);
+    for (int i = 0; i < n; i++) {
+        int cnt = ctx->h_counts[i];
+        memset(&res[i], 0, sizeof(tw_result));
+        res[i].code = TW_OK;
+        res[i].status = cnt == 0 ? TW_STATUS_OK : TW_STATUS_SUSPICIOUS;
+        res[i].n_vectors = cnt;
+        res[i].width = ctx->last_w; res[i].height = ctx->last_h;
+        res[i].time = ms * 1e-3f / n;
+        int ncopy = std::min(std::min(cnt, cap), ctx->dev_cap);
+        if (ncopy > 0 && out) {
+            e = cudaMemcpyAsync(out + (size_t)i * cap, (const tw_vector *)ctx->d_vectors + (size_t)i * ctx->dev_cap,
+                                sizeof(tw_vector) * ncopy, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e != cudaSuccess) { set_err(ctx, "fetch vectors", e); fill_error(&res[i], TW_CUDA_ERROR, ctx->err.c_str()); }
+        }
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "fetch sync", e); return TW_CUDA_ERROR; }
+    return TW_OK;
+}
+
+int tw_batch_flow(tw_ctx *ctx, int pair, float *flowx, float *flowy)
+{
+    if (!ctx || !ctx->ran || pair < 0 || pair >= ctx->last_n) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    const Scale &f = ctx->plan.scales.back();
+    const float *base = f.flow + (size_t)pair * 2 * f.d.plane;
+    cudaError_t e = cudaSuccess;
+    if (flowx) e = cudaMemcpy2DAsync(flowx, sizeof(float) * f.d.w, base, sizeof(float) * f.d.pitch, sizeof(float) * f.d.w, f.d.h,
+                                     cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && flowy)
+        e = cudaMemcpy2DAsync(flowy, sizeof(float) * f.d.w, base + f.d.plane, sizeof(float) * f.d.pitch, sizeof(float) * f.d.w,
+                              f.d.h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "flow D2H", e); return TW_CUDA_ERROR; }
+    return TW_OK;
+}
+
+int tw_flow(tw_ctx *ctx, const uint8_t *expect, const uint8_t *target, int w, int h, int stride, const tw_flow_param *param,
+            float *flowx, float *flowy, float *seconds)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    if (!expect || !target) { ctx->err = "null image"; return TW_BAD_IMAGE_FORMAT; }
+    int rc = upload_impl(ctx, 1, &expect, &target, w, h, stride, param);
+    if (rc != TW_OK) return rc;
+    rc = tw_batch_run(ctx, 1, w, h, param, 0.0, 0);
+    if (rc != TW_OK) return rc;
+    rc = tw_batch_flow(ctx, 0, flowx, flowy);
+    if (rc != TW_OK) return rc;
+    if (seconds) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_r0, ctx->ev_r1);
+        *seconds = ms * 1e-3f;
+    }
+    return TW_OK;
+}
+
+int tw_compare_batch(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride,
+                     const tw_flow_param *param, double threshold, int span, tw_vector *out, int cap, tw_result *res)
+{
+    if (!ctx || !res) return TW_BAD_PARAMETER;
+    auto fail_all = [&](int code, const char *msg) {
+        for (int i = 0; i < n; i++) fill_error(&res[i], code, msg);
+        return code;
+    };
+    if (span < 1) return fail_all(TW_BAD_PARAMETER, "span must be >= 1");
+    if (validate_param(param) != TW_OK) return fail_all(TW_BAD_PARAMETER, "bad optical-flow parameter");
+    int rc = upload_impl(ctx, n, expect, target, w, h, stride, param);
+    if (rc != TW_OK) return fail_all(rc, ctx->err.c_str());
+    rc = tw_batch_run(ctx, n, w, h, param, threshold, span);
+    if (rc != TW_OK) return fail_all(rc, ctx->err.c_str());
+    return tw_batch_fetch(ctx, n, out, cap, res);
+}
+
+int tw_compare(tw_ctx *ctx, const uint8_t *expect, int ew, int eh, const uint8_t *target, int tw_, int th_,
+               const tw_flow_param *param, double threshold, int span, tw_vector *out, int cap, tw_result *res)
+{
+    if (!res) return TW_BAD_PARAMETER;
+    if (!ctx) { fill_error(res, TW_BAD_PARAMETER, "null context"); return res->code; }
+    // src/opticalflow.cpp:37-49: an image that cannot be opened is BadImageFormat
+    if (!expect || ew < 1 || eh < 1) { fill_error(res, TW_BAD_IMAGE_FORMAT, "Can't open expected image"); return res->code; }
+    if (!target || tw_ < 1 || th_ < 1) { fill_error(res, TW_BAD_IMAGE_FORMAT, "Can't open target image"); return res->code; }
+    // src/opticalflow.cpp:52-61
+    if (abs(eh - th_) > 5 || abs(ew - tw_) > 5) { fill_error(res, TW_DONT_MATCH_SIZE, "Don't match image size"); return res->code; }
+    if (eh != th_ || ew != tw_) {
+        fill_error(res, TW_UNSUPPORTED, "size differs within 5 px: device resize of the target not implemented yet");
+        return res->code;
+    }
+    tw_compare_batch(ctx, 1, &expect, &target, ew, eh, ew, param, threshold, span, out, cap, res);
+    return res->code;
+}
+
+int tw_timer_start(tw_ctx *ctx)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    return cudaEventRecord(ctx->ev_t0, ctx->stream) == cudaSuccess ? TW_OK : TW_CUDA_ERROR;
+}
+
+int tw_timer_stop(tw_ctx *ctx, float *ms)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventRecord(ctx->ev_t1, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_t1);
+    if (e == cudaSuccess && ms) e = cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1);
+    if (e != cudaSuccess) { set_err(ctx, "timer", e); return TW_CUDA_ERROR; }
+    return TW_OK;
+}
+
+int tw_profile_enable(tw_ctx *ctx, int on)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_profile(ctx);
+    ctx->profiling = on != 0;
+    for (int i = 0; i < F_COUNT; i++) { ctx->fam_ms[i] = 0; ctx->fam_launches[i] = 0; ctx->fam_bytes[i] = 0; }
+    return TW_OK;
+}
+
+int tw_profile_read(tw_ctx *ctx, int max_n, const char **names, float *ms, int *launches, double *alg_bytes)
+{
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_profile(ctx);
+    int n = std::min(max_n, (int)F_COUNT);
+    for (int i = 0; i < n; i++) {
+        if (names) names[i] = kFamilyNames[i];
+        if (ms) ms[i] = ctx->fam_ms[i];
+        if (launches) launches[i] = ctx->fam_launches[i];
+        if (alg_bytes) alg_bytes[i] = ctx->fam_bytes[i];
+    }
+    return F_COUNT;
+}
+
+long long tw_launch_count(tw_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tw_debug_keep_levels(tw_ctx *ctx, int on)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    ctx->keep_levels = on ? 1 : 0;
+    return TW_OK;
+}
+
+int tw_debug_read(tw_ctx *ctx, const char *name, int scale, int pair, float *out, int cap_floats, int *w, int *h)
+{
+    if (!ctx || !ctx->ran || !name || !out) return -1;
+    Plan &pl = ctx->plan;
+    if (scale < 0 || scale >= (int)pl.scales.size() || pair < 0 || pair >= ctx->last_n) return -1;
+    cudaSetDevice(ctx->device);
+    const Scale &s = pl.scales[scale];
+    const float *base = nullptr;
+    int cn = 0;
+    if (!strcmp(name, "I0")) { base = s.I + (size_t)pair * 2 * s.d.plane; cn = 1; }
+    else if (!strcmp(name, "I1")) { base = s.I + ((size_t)pair * 2 + 1) * s.d.plane; cn = 1; }
+    else if (!strcmp(name, "R0")) { base = s.R + (size_t)pair * 10 * s.d.plane; cn = 5; }
+    else if (!strcmp(name, "R1")) { base = s.R + ((size_t)pair * 10 + 5) * s.d.plane; cn = 5; }
+    else if (!strcmp(name, "M")) {
+        // the buffer the last iteration kernel of this scale read (its input M)
+        int it = pl.p.pyrIterations;
+        const float *m = (it <= 1 || ((it - 1) % 2 == 0)) ? s.M0 : s.M1;
+        base = m + (size_t)pair * 5 * s.d.plane; cn = 5;
+    }
+    else if (!strcmp(name, "flow")) { base = s.flow + (size_t)pair * 2 * s.d.plane; cn = 2; }
+    else return -1;
+    if ((size_t)cn * s.d.w * s.d.h > (size_t)cap_floats) return -2;
+    if (w) *w = s.d.w;
+    if (h) *h = s.d.h;
+    for (int c = 0; c < cn; c++) {
+        cudaError_t e = cudaMemcpy2DAsync(out + (size_t)c * s.d.w * s.d.h, sizeof(float) * s.d.w, base + (size_t)c * s.d.plane,
+                                          sizeof(float) * s.d.pitch, sizeof(float) * s.d.w, s.d.h, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { set_err(ctx, "debug read", e); return -3; }
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -3;
+    return cn;
+}
+
+} // extern "C"

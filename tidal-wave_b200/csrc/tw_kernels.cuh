@@ -1,0 +1,95 @@
+// tw_kernels.cuh -- launch wrappers of the sm_100a kernel families.
+// Device layout: every tensor is PLANAR float32 with a row pitch that is a multiple of 32 floats (128 B):
+//   I    [B][2][h][pitch]        level images (expected, target)
+//   R    [B][2][5][h][pitch]     polynomial expansion coefficients (R0 = expected, R1 = target)
+//   M    [B][5][h][pitch]        (G11, G12, G22, h1, h2)
+//   flow [B][2][h][pitch]        (dx, dy)
+// A "plane" is h*pitch floats.  Batches are the outermost dimension; kernels index them with blockIdx.z.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tw {
+
+constexpr int kMaxPolyN = 15;    // radius of the polynomial expansion window
+constexpr int kMaxWinRadius = 32; // winSize/2
+
+struct PolyTables {
+    float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
+    double ig11, ig03, ig33, ig55;
+    int n;
+};
+
+struct WinTaps {
+    float k[kMaxWinRadius + 1];
+    int m;
+};
+
+struct LevelDims {
+    int w, h, pitch;
+    size_t plane; // h * pitch
+};
+
+// K1: u8 full-res frames -> float level image (pre-blur REFLECT_101 + bilinear downsample), SURVEY App. A.2.
+struct LevelImageArgs {
+    const uint8_t *src; // [nimg][H][spitch]
+    int W, H, spitch;
+    float *dst;         // [nimg][h][pitch]
+    LevelDims d;
+    const int *xi; const float *xf; const int *yi; const float *yf; // device tables, A.2b
+    const float *taps;  // device, ksize floats
+    int ksize;
+    int nimg;
+    int tile_w, tile_h; // output tile
+    int smem_w, smem_h; // source tile bound (before clamping)
+    int identity;       // w == W && h == H
+};
+cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a);
+
+// K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
+cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t);
+
+// K3: (coarse flow -> bilinear upsample * 1/pyrScale | zero) -> first update-matrices, App. A.1 + A.4.
+struct FirstUpdateArgs {
+    const float *coarse; // [B][2][ch][cpitch] or nullptr (coarsest scale: zero flow)
+    LevelDims cd;
+    const int *xi; const float *xf; const int *yi; const float *yf; // upsample tables
+    float inv_scale;
+    const float *R;  // [B][2][5] planes
+    float *M;        // [B][5] planes (nullptr: skip)
+    float *flow_out; // [B][2] planes (nullptr: skip; used when pyrIterations == 0)
+    LevelDims d;
+    int batch;
+};
+cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a);
+
+// K4/K5: window blur of M + 2x2 solve, then (not last) next update-matrices or (last) flow write.
+struct IterArgs {
+    const float *Min; // [B][5] planes
+    float *Mout;      // [B][5] planes (not last)
+    const float *R;   // [B][2][5] planes
+    float *flow;      // [B][2] planes (last)
+    LevelDims d;
+    int batch;
+    int last;
+};
+cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
+// Box window (flags == 0), App. A.6: vertical float-difference running sums in double (V planes), then
+// horizontal window + solve (+ update).
+cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *V, const LevelDims &d, int batch, int m);
+cudaError_t launch_box_iter(cudaStream_t s, const double *V, const IterArgs &a, int m, int winSize);
+
+// Span sampling + threshold classification + ordered compaction, reference src/consumer.cpp:60-77.
+struct SampleArgs {
+    const float *flow; // [B][2] planes, full-res
+    LevelDims d;
+    int batch;
+    int span;
+    double thr2; // threshold * threshold in double
+    int *counts;       // [B]
+    void *vectors;     // [B][cap] tw_vector {int x, int y, double dx, double dy}
+    int cap;
+};
+cudaError_t launch_sample(cudaStream_t s, const SampleArgs &a);
+
+} // namespace tw

@@ -1,0 +1,257 @@
+// tw_pool.cpp -- the dispatcher: a B200-native re-design of the reference's Manager + Consumer pool
+// (/root/reference/src/manager.cpp:40-98, src/consumer.cpp:12-94, src/message_queue.h:50-118).
+//
+// Reference semantics kept: N consumers block on ONE shared request queue; consumer i is bound to one
+// device for its whole life; options are fixed per pool; a response is produced for every request that a
+// consumer popped; stop() drops whatever is still queued and joins the consumers; Report counts
+// {request, data, error}.  Changed for the GPU: a consumer pops up to `batch` same-size requests at once and
+// runs them through one batched launch sequence; there is no CPU worker; results are kept in per-id slots
+// so the output does not depend on GPU count or completion order.
+#include "../../include/tidalwave_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct Request { // Request, src/message_queue.h:13-18 (paths replaced by decoded images)
+    long long id;
+    const uint8_t *expect, *target;
+    int ew, eh, tw, th;
+};
+
+struct Slot {
+    bool done = false, dropped = false;
+    tw_result res{};
+    std::vector<tw_vector> vectors;
+};
+
+} // namespace
+
+struct tw_pool {
+    tw_flow_param param{};
+    double threshold = 5.0;
+    int span = 10, batch = 1, vector_cap = 0, max_w = 0, max_h = 0;
+    std::vector<int> devices;
+    std::vector<std::thread> consumers;
+    std::mutex mu;
+    std::condition_variable cv_req, cv_res;
+    std::deque<Request> queue;
+    std::unordered_map<long long, Slot> slots;
+    bool running = true;
+    long long next_id = 0;
+    int request_count = 0, data_count = 0, error_count = 0; // Report, src/message_queue.h:44-48
+    std::atomic<int> ready{0};
+    std::string init_error;
+};
+
+namespace {
+
+void fill_error(tw_result *r, int code, const char *msg)
+{
+    memset(r, 0, sizeof *r);
+    r->code = code;
+    r->status = TW_STATUS_ERROR;
+    snprintf(r->reason, sizeof r->reason, "%s", msg);
+}
+
+void publish(tw_pool *p, long long id, const tw_result &res, const tw_vector *vec, int nvec)
+{
+    std::lock_guard<std::mutex> lk(p->mu);
+    Slot &s = p->slots[id];
+    s.res = res;
+    if (nvec > 0) s.vectors.assign(vec, vec + nvec);
+    s.done = true;
+    if (res.status == TW_STATUS_ERROR) p->error_count++; else p->data_count++; // Manager::notify, src/manager.cpp:109-114
+}
+
+// Consumer::run, src/consumer.cpp:42-94
+void consumer_main(tw_pool *p, int idx)
+{
+    char err[256] = {0};
+    tw_ctx *ctx = tw_create(p->devices[idx], p->max_w, p->max_h, p->batch, err, sizeof err);
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (!ctx) p->init_error = err;
+        p->ready.fetch_add(1);
+    }
+    p->cv_res.notify_all();
+    const int cap = p->vector_cap;
+    std::vector<tw_vector> vec((size_t)p->batch * std::max(cap, 1));
+    std::vector<tw_result> res(p->batch);
+    std::vector<Request> work;
+    std::vector<const uint8_t *> ex(p->batch), tg(p->batch);
+    for (;;) {
+        work.clear();
+        {
+            // MessageQueue::tryPop, src/message_queue.h:67-85: wait for a request or the stop notice
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_req.wait(lk, [&] { return !p->queue.empty() || !p->running; });
+            if (!p->running) break;
+            work.push_back(p->queue.front());
+            p->queue.pop_front();
+            // batch: take the following requests while they are compute-ready and have the same size
+            const Request &h = work[0];
+            bool head_ok = h.expect && h.target && h.ew == h.tw && h.eh == h.th;
+            while (head_ok && (int)work.size() < p->batch && !p->queue.empty()) {
+                const Request &q = p->queue.front();
+                if (!(q.expect && q.target && q.ew == h.ew && q.eh == h.eh && q.tw == h.ew && q.th == h.eh)) break;
+                work.push_back(q);
+                p->queue.pop_front();
+            }
+        }
+        if (!ctx) {
+            for (auto &r : work) {
+                tw_result e;
+                fill_error(&e, TW_CUDA_ERROR, err);
+                publish(p, r.id, e, nullptr, 0);
+            }
+            p->cv_res.notify_all();
+            continue;
+        }
+        if (work.size() == 1) {
+            const Request &r = work[0];
+            tw_compare(ctx, r.expect, r.ew, r.eh, r.target, r.tw, r.th, &p->param, p->threshold, p->span, vec.data(), cap, &res[0]);
+            publish(p, r.id, res[0], vec.data(), std::min(res[0].n_vectors, cap));
+        } else {
+            int n = (int)work.size();
+            for (int i = 0; i < n; i++) { ex[i] = work[i].expect; tg[i] = work[i].target; }
+            tw_compare_batch(ctx, n, ex.data(), tg.data(), work[0].ew, work[0].eh, work[0].ew, &p->param, p->threshold, p->span,
+                             vec.data(), cap, res.data());
+            for (int i = 0; i < n; i++)
+                publish(p, work[i].id, res[i], vec.data() + (size_t)i * cap, std::min(res[i].n_vectors, cap));
+        }
+        p->cv_res.notify_all();
+    }
+    if (ctx) tw_destroy(ctx);
+}
+
+int take(tw_pool *p, std::unordered_map<long long, Slot>::iterator it, tw_vector *out, int cap, tw_result *res)
+{
+    Slot &s = it->second;
+    if (s.dropped) { p->slots.erase(it); return -1; }
+    if (res) *res = s.res;
+    int n = std::min<int>((int)s.vectors.size(), cap);
+    if (out && n > 0) memcpy(out, s.vectors.data(), sizeof(tw_vector) * n);
+    int code = s.res.code;
+    p->slots.erase(it);
+    return code;
+}
+
+} // namespace
+
+extern "C" {
+
+tw_pool *tw_pool_create(const int *devices, int n_devices, int max_w, int max_h, int batch, const tw_flow_param *param,
+                        double threshold, int span, int vector_cap, char *err, int errlen)
+{
+    auto fail = [&](const char *m) -> tw_pool * {
+        if (err && errlen > 0) snprintf(err, errlen, "%s", m);
+        return nullptr;
+    };
+    if (!devices || n_devices < 1 || !param || span < 1 || batch < 1 || vector_cap < 0) return fail("bad pool parameter");
+    if (tw_device_count() < 1) return fail("no CUDA device (there is no CPU fallback worker)");
+    tw_pool *p = new tw_pool();
+    p->param = *param; p->threshold = threshold; p->span = span; p->batch = batch; p->vector_cap = vector_cap;
+    p->max_w = max_w; p->max_h = max_h;
+    p->devices.assign(devices, devices + n_devices);
+    // Manager::start, src/manager.cpp:55-59: one consumer per device entry
+    for (int i = 0; i < n_devices; i++) p->consumers.emplace_back(consumer_main, p, i);
+    {
+        std::unique_lock<std::mutex> lk(p->mu);
+        p->cv_res.wait(lk, [&] { return p->ready.load() == n_devices; });
+        if (!p->init_error.empty()) {
+            std::string m = p->init_error;
+            lk.unlock();
+            tw_pool_stop(p);
+            tw_pool_destroy(p);
+            return fail(m.c_str());
+        }
+    }
+    return p;
+}
+
+long long tw_pool_submit(tw_pool *p, const uint8_t *expect, int ew, int eh, const uint8_t *target, int tw_, int th_)
+{
+    if (!p) return -1;
+    long long id;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (!p->running) return -1;
+        id = p->next_id++;
+        p->slots[id];
+        p->queue.push_back(Request{id, expect, target, ew, eh, tw_, th_});
+        p->request_count++; // Manager::request, src/manager.cpp:75-76
+    }
+    p->cv_req.notify_one();
+    return id;
+}
+
+int tw_pool_wait(tw_pool *p, long long id, tw_vector *out, int cap, tw_result *res)
+{
+    if (!p) return -1;
+    std::unique_lock<std::mutex> lk(p->mu);
+    auto it = p->slots.find(id);
+    if (it == p->slots.end()) return -1;
+    p->cv_res.wait(lk, [&] { it = p->slots.find(id); return it == p->slots.end() || it->second.done || it->second.dropped; });
+    if (it == p->slots.end()) return -1;
+    return take(p, it, out, cap, res);
+}
+
+int tw_pool_poll(tw_pool *p, long long id, tw_vector *out, int cap, tw_result *res)
+{
+    if (!p) return -1;
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto it = p->slots.find(id);
+    if (it == p->slots.end()) return -1;
+    if (it->second.dropped) { p->slots.erase(it); return -1; }
+    if (!it->second.done) return 0;
+    take(p, it, out, cap, res);
+    return 1;
+}
+
+void tw_pool_report(tw_pool *p, int *request_count, int *data_count, int *error_count)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (request_count) *request_count = p->request_count;
+    if (data_count) *data_count = p->data_count;
+    if (error_count) *error_count = p->error_count;
+}
+
+void tw_pool_stop(tw_pool *p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (!p->running && p->consumers.empty()) return;
+        p->running = false;
+        // pending requests are dropped (tryPop returns false once stopped, src/message_queue.h:75-78)
+        for (auto &r : p->queue) p->slots[r.id].dropped = true;
+        p->queue.clear();
+    }
+    p->cv_req.notify_all();
+    p->cv_res.notify_all();
+    for (auto &t : p->consumers) if (t.joinable()) t.join();
+    p->consumers.clear();
+    p->cv_res.notify_all();
+}
+
+void tw_pool_destroy(tw_pool *p)
+{
+    if (!p) return;
+    tw_pool_stop(p);
+    delete p;
+}
+
+} // extern "C"
