@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: image pairs/sec at 1920x1080 (BASELINE.json), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A "step" = one pass of the whole hot path (pyramid, polynomial expansion, update-matrices, window blur + solve
+iterations, span sampling + classification) over one batch of B synthetic 1920x1080 pairs with the reference's
+default options (BASELINE.json configs[1]; the batch is configs[4]'s work-queue unit).
+
+  value     pairs/s with the batch already resident in HBM (device pass only, CUDA events on the library's stream)
+  e2e       pairs/s through the dispatcher API (tw_pool_*): pinned HOST images in, result structs out, H2D/D2H inside
+  roofline  dominant kernel family: algorithmic bytes / event-timed duration vs measured HBM peak
+  cpu_baseline  the reference's CPU path (cv2 calcOpticalFlowFarneback, else the C oracle port) on this box's cores
+
+Multi-GPU: pairs are independent => each rank runs its own shard (weak scaling), no data-path collective; torch.distributed
+is used only for the barrier and the max-over-ranks of the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+METRIC = "image pairs/sec at 1920x1080"
+UNIT = "pairs/s"
+
+
+def measured_peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples in the top half of what we saw (idle samples at the edges are dropped)
+        if sm:
+            hi = [s for s in sm if s >= 0.5 * max(sm)]
+            med = float(np.median(hi))
+        else:
+            med = None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pool(n: int):
+    import tidalwave_b200 as tw
+    return tw.synth.pool_pairs(n, W, H, seed0=100)
+
+
+def cpu_reference(pairs, n_pairs: int, workers: int):
+    """The reference's CPU path on host cores: Farneback + sampling per pair, parallel ACROSS pairs like the
+    reference's consumer pool (src/manager.cpp:55-59).  Returns (pairs/s, kind, description)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import FlowParam, RefOracle, sample_numpy
+    try:
+        import cv2
+        cv2.ipp.setUseIPP(False)
+        cv2.setNumThreads(1)
+        impl = f"cv2 {cv2.__version__} calcOpticalFlowFarneback (the reference's third-party library, IPP off, 1 thread/pair) + sampling"
+
+        def one(i):
+            a, b = pairs[i % len(pairs)]
+            fl = cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 30, 3, 7, 1.5, 256)
+            return sample_numpy(fl)[0]
+    except Exception:
+        O = RefOracle()
+        impl = "oracle/farneback_ref.c (scalar C port) + sampling"
+
+        def one(i):
+            a, b = pairs[i % len(pairs)]
+            return O.sample(O.farneback(a, b, FlowParam()))[0]
+    one(0)  # warm
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(one, range(n_pairs)))
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, "port", f"{n_pairs} pairs of the 1920x1080 pool, {workers} threads across pairs; {impl}"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = cores
+    pairs = make_pool(4)
+    per_step = max(workers, 4)
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, kind, desc = cpu_reference(pairs, per_step, workers)
+        if s >= args.warmup:
+            vals.append(v)
+        if s == 0 and per_step / v > 60:  # keep the whole run within a few minutes
+            per_step = max(workers // 2, 2)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic 1920x1080 pairs, default options (threshold 5, span 10, pyrLevels 3, winSize 30, "
+                                   "polyN 7, flags 256)", "pairs_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local_rank)
+        try:
+            dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        except Exception:
+            dist_.init_process_group("gloo")
+        dist = dist_
+
+    import tidalwave_b200 as tw
+    lib = tw.load()
+    B = args.batch
+    pairs = make_pool(B)  # every rank: same seeded pool, its own copy (weak scaling: B pairs per step per GPU)
+    of = tw.OpticalFlow(local_rank, W, H, B)
+    param = tw.OpticalFlowParameter()
+    cp = param.c()
+    threshold, span = 5.0, 10
+
+    # pinned host copies of the pool
+    npx = W * H
+    pinned = []
+    for a, b in pairs:
+        pa = lib.tw_host_alloc(npx); pb = lib.tw_host_alloc(npx)
+        C.memmove(pa, a.ctypes.data, npx); C.memmove(pb, b.ctypes.data, npx)
+        pinned.append((pa, pb))
+    ex = (C.c_void_p * B)(*[p[0] for p in pinned])
+    tg = (C.c_void_p * B)(*[p[1] for p in pinned])
+    cap = ((W + span - 1) // span) * ((H + span - 1) // span)
+    vec = (tw.tw_vector * (cap * B))()
+    res = (tw.tw_result * B)()
+
+    def check(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: rc={rc} {of.last_error()}")
+
+    # ---- device-resident pass: inputs in HBM before the timed region ----
+    check(lib.tw_batch_upload(of.ctx, B, ex, tg, W, H, W), "upload")
+    check(lib.tw_sync(of.ctx), "sync")
+
+    def step():
+        check(lib.tw_l2_flush(of.ctx), "flush")
+        check(lib.tw_batch_run(of.ctx, B, W, H, C.byref(cp), threshold, span), "run")
+
+    for _ in range(args.warmup):
+        step()
+    check(lib.tw_sync(of.ctx), "sync")
+    # sanity: the warm-up results are real
+    check(lib.tw_batch_fetch(of.ctx, B, vec, cap, res), "fetch")
+    statuses = [res[i].status for i in range(B)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    of.profile(True)
+    l0 = of.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    check(lib.tw_sync(of.ctx), "sync")
+    check(lib.tw_timer_start(of.ctx), "timer")
+    for _ in range(args.steps):
+        step()
+    ms = C.c_float(0)
+    check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")  # records + synchronises the stream
+    barrier()
+    clocks = sampler.stop()
+    launches = of.launch_count() - l0
+    prof = of.profile_read()
+    of.profile(False)
+    elapsed_ms = float(ms.value)
+    if dist is not None:
+        import torch
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel family ----
+    peak, peak_src = measured_peaks()
+    fams = {k: v for k, v in prof.items() if v["launches"] > 0}
+    top = max(fams, key=lambda k: fams[k]["ms"])
+    tv = fams[top]
+    achieved = tv["alg_bytes"] / (tv["ms"] * 1e-3) / 1e9
+    kernel_ms_total = sum(v["ms"] for v in fams.values())
+    alg_total = sum(v["alg_bytes"] for v in fams.values())
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": tv["ms"] / tv["launches"],
+                "alg_bytes_per_launch": tv["alg_bytes"] / tv["launches"], "share_of_step": tv["ms"] / kernel_ms_total,
+                "pipeline": {"alg_bytes_per_pair": alg_total / (B * args.steps), "achieved": alg_total / (elapsed_ms * 1e-3) / 1e9,
+                             "frac": alg_total / (elapsed_ms * 1e-3) / 1e9 / peak},
+                "families": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                 "GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in fams.items()}}
+
+    # ---- e2e: dispatcher API, pinned host images in, result structs out ----
+    e2e = None
+    if not args.no_e2e:
+        n_req = B * max(4, min(args.steps, 12))
+        perr = C.create_string_buffer(256)
+        dv = (C.c_int * 2)(local_rank, local_rank)  # two consumers per GPU: one uploads while the other computes
+        pool = lib.tw_pool_create(dv, 2, W, H, B, C.byref(cp), threshold, span, 4096, perr, 256)
+        if not pool:
+            raise RuntimeError("tw_pool_create: " + perr.value.decode())
+        rvec = (tw.tw_vector * 4096)()
+        rres = tw.tw_result()
+
+        def run_pool(n):
+            ids = [lib.tw_pool_submit(pool, pinned[i % B][0], W, H, pinned[i % B][1], W, H) for i in range(n)]
+            nv = 0
+            for i in ids:
+                rc = lib.tw_pool_wait(pool, i, rvec, 4096, C.byref(rres))
+                if rc != 0:
+                    raise RuntimeError(f"pool wait rc={rc} {rres.reason.decode()}")
+                nv += min(rres.n_vectors, 4096)
+            return nv
+
+        run_pool(2 * B)  # warm-up (plans, buffers)
+        barrier()
+        t0 = time.perf_counter()
+        nv = run_pool(n_req)
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        lib.tw_pool_destroy(pool)
+        e2e = {"value": world * n_req / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * npx * B,
+               "d2h_bytes_per_step": int(4 * B + 24 * nv * B / n_req), "pairs": n_req,
+               "api": "tw_pool_submit/tw_pool_wait, 2 consumers per GPU, batch %d, pinned host images" % B}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_pairs = max(cores, 8)
+        v, kind, desc = cpu_reference(pairs, n_pairs, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]/[4]: batch of %d synthetic 1920x1080 pairs per step per GPU (seeded S/T pool, true shift "
+                                       "(-0.37,+0.61) px, every 8th with a defect), default options (threshold 5, span 10, pyrLevels 3, "
+                                       "winSize 30, pyrIterations 3, polyN 7, polySigma 1.5, flags 256)" % B,
+                           "batch": B, "parallelism": "independent pairs per GPU, no collective",
+                           "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "statuses": statuses}
+        print(json.dumps(line), flush=True)
+    of.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,8 @@ void *tw_host_alloc(size_t bytes);
 void tw_host_free(void *p);
 
 /* ---- measurement hooks (CUDA events on the context's own stream) ---- */
+/* Enqueues a write of a >L2 (256 MB) scratch buffer on the context's stream, evicting L2 between timed steps. */
+int tw_l2_flush(tw_ctx *ctx);
 int tw_timer_start(tw_ctx *ctx);
 int tw_timer_stop(tw_ctx *ctx, float *ms);       /* records, synchronises, returns elapsed ms */
 /* Per-kernel-family event timing: enable, run, then read n families back.  names[i] points to a static

@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     L.tw_host_alloc.restype = C.c_void_p
     L.tw_host_alloc.argtypes = [C.c_size_t]
     L.tw_host_free.argtypes = [C.c_void_p]
+    L.tw_l2_flush.argtypes = [C.c_void_p]
     L.tw_timer_start.argtypes = [C.c_void_p]
     L.tw_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tw_profile_enable.argtypes = [C.c_void_p, C.c_int]

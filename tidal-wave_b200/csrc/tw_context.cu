@@ -72,6 +72,8 @@ struct tw_ctx {
     int fam_launches[F_COUNT] = {0};
     double fam_bytes[F_COUNT] = {0};
     long long launches = 0;
+    void *flush_buf = nullptr;
+    int flush_val = 0;
     std::string err;
 };
 
@@ -517,6 +519,7 @@ void tw_destroy(tw_ctx *ctx)
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->d_vectors) cudaFree(ctx->d_vectors);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->ev_r0) cudaEventDestroy(ctx->ev_r0);
@@ -707,6 +710,21 @@ int tw_compare(tw_ctx *ctx, const uint8_t *expect, int ew, int eh, const uint8_t
     }
     tw_compare_batch(ctx, 1, &expect, &target, ew, eh, ew, param, threshold, span, out, cap, res);
     return res->code;
+}
+
+int tw_l2_flush(tw_ctx *ctx)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    const size_t bytes = (size_t)256 << 20;
+    if (!ctx->flush_buf) {
+        cudaError_t e = cudaMalloc(&ctx->flush_buf, bytes);
+        if (e != cudaSuccess) { set_err(ctx, "flush alloc", e); return TW_CUDA_ERROR; }
+    }
+    ctx->flush_val ^= 1;
+    cudaError_t e = cudaMemsetAsync(ctx->flush_buf, ctx->flush_val, bytes, ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "flush", e); return TW_CUDA_ERROR; }
+    return TW_OK;
 }
 
 int tw_timer_start(tw_ctx *ctx)

@@ -199,6 +199,9 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 // ------------------------------------------------------------------------------------------------
 // A.4  update matrices for one pixel.  All float, no FMA.  R0/R1 point at channel 0 of the pair's planes.
 // ------------------------------------------------------------------------------------------------
+// border damping {0.14, 0.14, 0.4472, 0.4472, 0.4472} indexed by the distance to the edge (App. A.4)
+__device__ __forceinline__ float border_tab(int i) { return i < 2 ? 0.14f : 0.4472f; }
+
 __device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane,
                                                    int pitch, int w, int h, int x, int y, float dx, float dy, float m[5])
 {
@@ -231,9 +234,8 @@ __device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0,
     r2 = r2 + (r4 * dy + r6 * dx);
     r3 = r3 + (r6 * dy + r5 * dx);
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float tab[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        float sc = (x < 5 ? tab[x] : 1.f) * (x >= w - 5 ? tab[w - x - 1] : 1.f) * (y < 5 ? tab[y] : 1.f) *
-                   (y >= h - 5 ? tab[h - y - 1] : 1.f);
+        float sc = (x < 5 ? border_tab(x) : 1.f) * (x >= w - 5 ? border_tab(w - x - 1) : 1.f) * (y < 5 ? border_tab(y) : 1.f) *
+                   (y >= h - 5 ? border_tab(h - y - 1) : 1.f);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     m[0] = r4 * r4 + r6 * r6;
@@ -362,8 +364,146 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4/K5 (window radius MR = 15 or 7)  register-blocked Gaussian window blur + solve + update.
+//   tile 96 x 32 outputs, 256 threads, 2 CTAs / SM.
+//   phase V: thread = (column, 16-row group); 16+2*MR inputs in registers (coalesced global loads, row/column
+//            replicate = clamped addresses), 16 outputs, taps summed in the oracle's order; -> shared Vb[5][32][132]
+//   phase H: lane = row (pitch 132 = 4 mod 32 words: conflict-free LDS.128), warp = 12-column segment, 3 groups of
+//            4 pixels x 5 channels; 2x2 solve in double; flow -> shared Fb[2][32][97]
+//   phase U: lane = x (coalesced): next update-matrices (A.4) or, last iteration, the flow write.
+// FMA = validated relaxation (fmaf in the tap sums, SURVEY App. B.5: <= 2e-4 px on the default options); the
+// default build keeps the oracle's add-mul-add order bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_RV = 16;
+constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
+
+template <int MR, bool FMA>
+__global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps t)
+{
+    extern __shared__ __align__(16) float gk_smem[];
+    float *Vb = gk_smem;
+    float *Fb = gk_smem + 5 * GK_TH * GK_VP;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = blockIdx.x * GK_TW, y0 = blockIdx.y * GK_TH, b = blockIdx.z;
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const size_t plane = a.d.plane;
+    const float *Min = a.Min + (size_t)b * 5 * plane;
+
+    // ---- phase V ----
+    {
+        const int j = tid & (GK_VW - 1), g = tid >> 7;
+        const int gx = clampi(x0 - 16 + j, 0, w - 1);
+        const int ybase = y0 + g * GK_RV - MR;
+        const bool interior = ybase >= 0 && ybase + GK_RV + 2 * MR - 1 <= h - 1;
+#pragma unroll 1
+        for (int c = 0; c < 5; c++) {
+            const float *Mc = Min + c * plane + gx;
+            float in[GK_RV + 2 * MR];
+            if (interior) {
+                const float *p = Mc + (size_t)ybase * pitch;
+#pragma unroll
+                for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(p + (size_t)r * pitch);
+            } else {
+#pragma unroll
+                for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(Mc + (size_t)clampi(ybase + r, 0, h - 1) * pitch);
+            }
+            float *dst = Vb + (c * GK_TH + g * GK_RV) * GK_VP + j;
+#pragma unroll
+            for (int o = 0; o < GK_RV; o++) {
+                float v = in[o + MR] * t.k[0];
+#pragma unroll
+                for (int i = 1; i <= MR; i++) {
+                    if (FMA) v = fmaf(in[o + MR + i] + in[o + MR - i], t.k[i], v);
+                    else v = v + (in[o + MR + i] + in[o + MR - i]) * t.k[i];
+                }
+                dst[o * GK_VP] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase H + solve ----
+    {
+        const int seg = tid >> 5; // 12-column segment
+        constexpr int LO = (16 - MR) & ~3;                // first needed index, 16B-aligned
+        constexpr int NV = ((3 + 16 + MR) | 3) + 1 - LO;  // floats loaded per channel per group (multiple of 4)
+#pragma unroll 1
+        for (int grp = 0; grp < 3; grp++) {
+            const int cbase = seg * 12 + grp * 4; // output column of pixel 0; V column = cbase + 16
+            float res[5][4];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float4 *src = reinterpret_cast<const float4 *>(Vb + (c * GK_TH + lane) * GK_VP + cbase + LO);
+                float v[NV];
+#pragma unroll
+                for (int q = 0; q < NV / 4; q++) {
+                    float4 u = src[q];
+                    v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int ctr = p + 16 - LO;
+                    float s = v[ctr] * t.k[0];
+#pragma unroll
+                    for (int i = 1; i <= MR; i++) {
+                        if (FMA) s = fmaf(t.k[i], v[ctr - i] + v[ctr + i], s);
+                        else s = s + t.k[i] * (v[ctr - i] + v[ctr + i]);
+                    }
+                    res[c][p] = s;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float fx, fy;
+                solve2x2(res[0][p], res[1][p], res[2][p], res[3][p], res[4][p], fx, fy);
+                Fb[lane * GK_FP + cbase + p] = fx;
+                Fb[(GK_TH + lane) * GK_FP + cbase + p] = fy;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase U: coalesced epilogue ----
+    const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
+#pragma unroll 1
+    for (int i = tid; i < GK_TW * GK_TH; i += 256) {
+        const int row = i / GK_TW, col = i - row * GK_TW;
+        const int x = x0 + col, y = y0 + row;
+        if (x >= w || y >= h) continue;
+        const float fx = Fb[row * GK_FP + col], fy = Fb[(GK_TH + row) * GK_FP + col];
+        const size_t o = (size_t)y * pitch + x;
+        if (a.last) {
+            float *f = a.flow + (size_t)b * 2 * plane;
+            f[o] = fx; f[o + plane] = fy;
+        } else {
+            float mm[5];
+            update_matrices_px(R0, R1, plane, pitch, w, h, x, y, fx, fy, mm);
+            float *M = a.Mout + (size_t)b * 5 * plane;
+#pragma unroll
+            for (int c = 0; c < 5; c++) M[o + c * plane] = mm[c];
+        }
+    }
+}
+
+template <int MR, bool FMA>
+static cudaError_t launch_gauss_fast(cudaStream_t s, const IterArgs &a, const WinTaps &t)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gauss_iter_kernel<MR, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GK_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
+    gauss_iter_kernel<MR, FMA><<<grid, 256, GK_SMEM, s>>>(a, t);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
+    if (t.m == 15) return a.fma ? launch_gauss_fast<15, true>(s, a, t) : launch_gauss_fast<15, false>(s, a, t);
+    if (t.m == 7) return a.fma ? launch_gauss_fast<7, true>(s, a, t) : launch_gauss_fast<7, false>(s, a, t);
     dim3 grid((a.d.w + GI_TW - 1) / GI_TW, (a.d.h + GI_TH - 1) / GI_TH, a.batch);
     size_t smem = sizeof(float) * GI_TH * (GI_TW + 2 * t.m);
     gauss_iter_generic_kernel<<<grid, 256, smem, s>>>(a, t);

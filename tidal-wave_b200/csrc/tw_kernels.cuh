@@ -72,6 +72,7 @@ struct IterArgs {
     LevelDims d;
     int batch;
     int last;
+    int fma; // validated relaxation: fmaf in the Gaussian tap sums (never set for the box window)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
 // Box window (flags == 0), App. A.6: vertical float-difference running sums in double (V planes), then
