@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gauss-fma", action="store_true", help="opt-in validated relaxation (tw_set_option gauss_fma)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -185,6 +186,8 @@ def main():
     B = args.batch
     pairs = make_pool(B)  # every rank: same seeded pool, its own copy (weak scaling: B pairs per step per GPU)
     of = tw.OpticalFlow(local_rank, W, H, B)
+    if args.gauss_fma:
+        of.set_option("gauss_fma", 1)
     param = tw.OpticalFlowParameter()
     cp = param.c()
     threshold, span = 5.0, 10
@@ -315,7 +318,7 @@ def main():
                 "config": {"workload": "configs[1]/[4]: batch of %d synthetic 1920x1080 pairs per step per GPU (seeded S/T pool, true shift "
                                        "(-0.37,+0.61) px, every 8th with a defect), default options (threshold 5, span 10, pyrLevels 3, "
                                        "winSize 30, pyrIterations 3, polyN 7, polySigma 1.5, flags 256)" % B,
-                           "batch": B, "parallelism": "independent pairs per GPU, no collective",
+                           "batch": B, "arithmetic": "gauss_fma relaxation" if args.gauss_fma else "bit-faithful operation order", "parallelism": "independent pairs per GPU, no collective",
                            "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "statuses": statuses}

@@ -116,6 +116,10 @@ int tw_sync(tw_ctx *ctx);
 /* Copies the dense flow planes of pair `pair` of the last run back (either pointer may be NULL). */
 int tw_batch_flow(tw_ctx *ctx, int pair, float *flowx, float *flowy);
 const char *tw_last_error(tw_ctx *ctx);
+/* Opt-in arithmetic relaxations (default 0 = bit-faithful to the oracle's operation order):
+ *   "gauss_fma" = 1: fused multiply-add in the Gaussian window tap sums (<= 2e-4 px on the
+ *                    default options; never applied to the box window). */
+int tw_set_option(tw_ctx *ctx, const char *name, int value);
 
 /* Pinned (page-locked) host memory for image buffers: H2D copies from it are true async DMA. */
 void *tw_host_alloc(size_t bytes);

@@ -89,6 +89,7 @@ def load() -> C.CDLL:
     L.tw_host_alloc.argtypes = [C.c_size_t]
     L.tw_host_free.argtypes = [C.c_void_p]
     L.tw_l2_flush.argtypes = [C.c_void_p]
+    L.tw_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.tw_timer_start.argtypes = [C.c_void_p]
     L.tw_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tw_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -155,6 +156,10 @@ class OpticalFlow:
             self.ctx = None
 
     __del__ = close
+
+    def set_option(self, name: str, value: int):
+        if self.lib.tw_set_option(self.ctx, name.encode(), int(value)) != 0:
+            raise ValueError(self.last_error())
 
     def last_error(self) -> str:
         return self.lib.tw_last_error(self.ctx).decode()

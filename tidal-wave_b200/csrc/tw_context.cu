@@ -56,6 +56,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
+    int opt_gauss_fma = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -202,7 +203,10 @@ void poly_tables(int n, double sigma, PolyTables &t)
     invert6(G, inv);
     t.n = n;
     t.ig11 = inv[1][1]; t.ig03 = inv[0][3]; t.ig33 = inv[3][3]; t.ig55 = inv[5][5];
-    for (int x = 0; x <= n; x++) { t.g[x] = g[x]; t.xg[x] = xg[x]; t.xxg[x] = xxg[x]; }
+    for (int x = 0; x <= n; x++) {
+        t.g[x] = g[x]; t.xg[x] = xg[x]; t.xxg[x] = xxg[x];
+        t.gd[x] = (double)g[x]; t.xxgd[x] = (double)xxg[x];
+    }
 }
 
 // SURVEY App. A.5 window taps.
@@ -226,7 +230,7 @@ int validate_param(const tw_flow_param *p)
     if (!p) return TW_BAD_PARAMETER;
     if (!(p->pyrScale > 0 && p->pyrScale < 1)) return TW_BAD_PARAMETER;
     if (p->pyrLevels < 0 || p->pyrLevels > 14) return TW_BAD_PARAMETER;
-    if (p->polyN != 5 && p->polyN != 7) return TW_BAD_PARAMETER;
+    if (p->polyN < 1 || p->polyN > kMaxPolyN) return TW_BAD_PARAMETER;
     if (p->flags != 0 && p->flags != 256) return TW_BAD_PARAMETER;
     if (p->winSize < 2 || p->winSize / 2 > kMaxWinRadius) return TW_BAD_PARAMETER;
     if (p->pyrIterations < 0 || p->pyrIterations > 100) return TW_BAD_PARAMETER;
@@ -284,21 +288,24 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         resize_coeffs(H, s.d.h, yi, yf);
         s.identity = (s.d.w == W && s.d.h == H);
         const int c = s.ksize / 2;
-        // choose an output tile whose source tile fits comfortably in shared memory
-        int tw_ = 32, th_ = 8;
+        // choose an output tile whose float source tile + row-pass buffer leave room for >= 2 CTAs per SM
+        int tw_ = s.identity ? 128 : 64, th_ = 16;
         for (;;) {
             int sw = 0, sh = 0;
             for (int d0 = 0; d0 < s.d.w; d0 += tw_) {
                 int d1 = std::min(d0 + tw_, s.d.w) - 1;
-                sw = std::max(sw, (xi[d1] + 1 + c) - (xi[d0] - c) + 1);
+                sw = std::max(sw, std::min(xi[d1] + 1, W - 1) + c - (xi[d0] - c) + 1);
             }
             for (int e0 = 0; e0 < s.d.h; e0 += th_) {
                 int e1 = std::min(e0 + th_, s.d.h) - 1;
-                sh = std::max(sh, (yi[e1] + 1 + c) - (yi[e0] - c) + 1);
+                sh = std::max(sh, std::min(yi[e1] + 1, H - 1) + c - (yi[e0] - c) + 1);
             }
-            sw = std::min(sw, W); sh = std::min(sh, H);
-            size_t bytes = (size_t)sh * ((sw + 3) & ~3) + 16 + sizeof(float) * ((size_t)sh * tw_ * 2 + s.ksize);
-            if (bytes <= 96 * 1024 || (tw_ == 1 && th_ == 1)) { s.smem_w = sw; s.smem_h = sh; break; }
+            size_t bytes = level_image_smem_bytes(sw, sh, tw_, s.ksize, s.identity);
+            if (bytes <= 64 * 1024 || (tw_ == 1 && th_ == 1)) {
+                if (bytes > 200 * 1024) { ctx->err = "pre-blur kernel too large for shared memory"; return false; }
+                s.smem_w = sw; s.smem_h = sh;
+                break;
+            }
             if (tw_ >= th_ * 2 && tw_ > 1) tw_ /= 2; else if (th_ > 1) th_ /= 2; else tw_ /= 2;
         }
         s.tile_w = tw_; s.tile_h = th_;
@@ -406,6 +413,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         la.xi = s.img_xi; la.xf = s.img_xf; la.yi = s.img_yi; la.yf = s.img_yf; la.taps = s.taps; la.ksize = s.ksize;
         la.nimg = 2 * n; la.tile_w = s.tile_w; la.tile_h = s.tile_h; la.smem_w = s.smem_w; la.smem_h = s.smem_h;
         la.identity = s.identity;
+        la.small = (s.ksize / 2 + 2 >= std::min(W, H));
         // I planes of a batch are laid out [B][2]: the u8 source is [B][2] too, so image index = blockIdx.z.
         LAUNCH(F_LEVEL, n * (2 * P0 + 8 * Pl), launch_level_image(ctx->stream, la));
         LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly));
@@ -427,6 +435,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             IterArgs ia{};
             ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
             ia.last = (it == p.pyrIterations - 1);
+            ia.fma = ctx->opt_gauss_fma;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
             if (p.flags & 256) {
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
@@ -773,6 +782,14 @@ int tw_profile_read(tw_ctx *ctx, int max_n, const char **names, float *ms, int *
 }
 
 long long tw_launch_count(tw_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tw_set_option(tw_ctx *ctx, const char *name, int value)
+{
+    if (!ctx || !name) return TW_BAD_PARAMETER;
+    if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
+    ctx->err = std::string("unknown option ") + name;
+    return TW_BAD_PARAMETER;
+}
 
 int tw_debug_keep_levels(tw_ctx *ctx, int on)
 {

@@ -19,111 +19,145 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
+// single-bounce REFLECT_101, valid for -len < p < 2*len - 1
+__device__ __forceinline__ int reflect1(int p, int len)
+{
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1  level image: u8 -> float, GaussianBlur(ksize) REFLECT_101 (rows first, then columns), bilinear
 //     resize to (w, h).  One block = one output tile; the u8 source tile (with halo) is staged in shared
 //     memory, the row pass is evaluated only at the source columns the resize reads, the column pass
 //     only at the source rows it reads.   SURVEY App. A.2 / A.2a / A.2b.
 // ------------------------------------------------------------------------------------------------
+// exact u8 -> float without the XU pipe: 0x4B000000 | b is 8388608.0f + b.
+__device__ __forceinline__ float u8_to_float(unsigned b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+
+template <bool IDENT>
 __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = a.ksize / 2;
+    extern __shared__ __align__(16) float li_smem[];
+    const int K = a.ksize, c = K / 2;
     const int d0 = blockIdx.x * a.tile_w, e0 = blockIdx.y * a.tile_h;
     const int d1 = min(d0 + a.tile_w, a.d.w) - 1, e1 = min(e0 + a.tile_h, a.d.h) - 1;
     const int tw_ = d1 - d0 + 1, th_ = e1 - e0 + 1;
     const int W = a.W, H = a.H;
-    // source extents
-    const int xs0 = a.xi[d0], xs1 = min(a.xi[d1] + 1, W - 1);
-    const int ys0 = a.yi[e0], ys1 = min(a.yi[e1] + 1, H - 1);
-    const int cx_lo = max(0, xs0 - c), cx_hi = min(W - 1, xs1 + c);
-    const int ry_lo = max(0, ys0 - c), ry_hi = min(H - 1, ys1 + c);
-    const int SW = cx_hi - cx_lo + 1, SH = ry_hi - ry_lo + 1;
-    const int SWp = (a.smem_w + 3) & ~3;
-    const int NC = a.identity ? a.tile_w : a.tile_w * 2;
-    unsigned char *stile = smem_raw;                                            // [smem_h][SWp]
-    float *rp = reinterpret_cast<float *>(smem_raw + (((size_t)a.smem_h * SWp + 15) & ~(size_t)15)); // [smem_h][NC]
-    float *ktab = rp + (size_t)a.smem_h * NC;                                   // [ksize]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // source tile (unclamped extents; border pixels are staged through REFLECT_101 so the tap loops index directly)
+    const int xs_lo = a.xi[d0] - c, ys_lo = a.yi[e0] - c;
+    const int SW = min(a.xi[d1] + 1, W - 1) + c - xs_lo + 1, SH = min(a.yi[e1] + 1, H - 1) + c - ys_lo + 1;
+    const int SWp = a.smem_w | 1; // odd pitch
+    const int NC = IDENT ? a.tile_w : a.tile_w * 2;
+    float *tile = li_smem;                        // [smem_h][SWp]
+    float *rp = tile + (size_t)a.smem_h * SWp;    // [smem_h][NC]
+    float *ktab = rp + (size_t)a.smem_h * NC;     // [K]
 
     const uint8_t *src = a.src + (size_t)blockIdx.z * H * a.spitch;
-    for (int i = threadIdx.x; i < a.ksize; i += blockDim.x) ktab[i] = a.taps[i];
-    for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) {
-        int r = i / SW, q = i - r * SW;
-        stile[r * SWp + q] = src[(size_t)(ry_lo + r) * a.spitch + cx_lo + q];
-    }
-    __syncthreads();
-
-    // row pass at the needed columns
-    const int ncol = a.identity ? tw_ : tw_ * 2;
-    for (int i = threadIdx.x; i < SH * ncol; i += blockDim.x) {
-        int r = i / ncol, slot = i - r * ncol;
-        int xcol;
-        if (a.identity) xcol = d0 + slot;
-        else xcol = min(a.xi[d0 + (slot >> 1)] + (slot & 1), W - 1);
-        const unsigned char *row = stile + r * SWp - cx_lo;
-        float o;
-        if (a.ksize == 3) {
-            float L = (float)row[reflect101(xcol - 1, W)], C = (float)row[xcol], Rr = (float)row[reflect101(xcol + 1, W)];
-            o = fmaf(C, ktab[1], (L + Rr) * ktab[0]);
-        } else {
-            o = (float)row[reflect101(xcol - c, W)] * ktab[0];
-            for (int j = 1; j < a.ksize; j++) o = fmaf((float)row[reflect101(xcol - c + j, W)], ktab[j], o);
+    for (int i = threadIdx.x; i < K; i += 256) ktab[i] = a.taps[i];
+    if (a.small) { // image smaller than the blur radius: REFLECT_101 may bounce more than once
+        for (int r = warp; r < SH; r += 8) {
+            const uint8_t *srow = src + (size_t)reflect101(ys_lo + r, H) * a.spitch;
+            for (int q = lane; q < SW; q += 32) tile[r * SWp + q] = u8_to_float(srow[reflect101(xs_lo + q, W)]);
         }
-        rp[r * NC + slot] = o;
-    }
-    __syncthreads();
-
-    // column pass at the needed rows + bilinear
-    float *dst = a.dst + (size_t)blockIdx.z * a.d.plane;
-    for (int i = threadIdx.x; i < tw_ * th_; i += blockDim.x) {
-        int ty = i / tw_, tx = i - ty * tw_;
-        int d = d0 + tx, e = e0 + ty;
-        int y0 = a.yi[e], y1 = min(y0 + 1, H - 1);
-        float res[2][2];
-        const int nyy = a.identity ? 1 : 2, nxx = a.identity ? 1 : 2;
-        for (int yy = 0; yy < nyy; yy++) {
-            int y = yy ? y1 : y0;
-            for (int xx = 0; xx < nxx; xx++) {
-                int slot = a.identity ? tx : tx * 2 + xx;
-                const float *col = rp + slot - (size_t)ry_lo * NC; // col[y*NC]
-                float o;
-                if (a.ksize == 3) {
-                    float U = col[reflect101(y - 1, H) * NC], C = col[y * NC], D = col[reflect101(y + 1, H) * NC];
-                    o = fmaf(U + D, ktab[0], C * ktab[1]);
-                } else {
-                    o = col[y * NC] * ktab[c];
-                    for (int j = 1; j <= c; j++)
-                        o = fmaf(col[reflect101(y - j, H) * NC] + col[reflect101(y + j, H) * NC], ktab[c + j], o);
-                }
-                res[yy][xx] = o;
+    } else {
+        // independent byte loads (ld.global.nc), 2 rows x 4 columns in flight per thread: this phase is latency-bound
+        for (int r = warp; r < SH; r += 16) {
+            const int r2 = min(r + 8, SH - 1);
+            const uint8_t *srow0 = src + (size_t)reflect1(ys_lo + r, H) * a.spitch;
+            const uint8_t *srow1 = src + (size_t)reflect1(ys_lo + r2, H) * a.spitch;
+#pragma unroll 4
+            for (int q = lane; q < SW; q += 32) {
+                const int gx = reflect1(xs_lo + q, W);
+                const unsigned b0 = __ldg(srow0 + gx), b1 = __ldg(srow1 + gx);
+                tile[r * SWp + q] = u8_to_float(b0);
+                tile[r2 * SWp + q] = u8_to_float(b1);
             }
         }
-        float out;
-        if (a.identity) {
-            out = res[0][0];
-        } else {
-            float fx = a.xf[d], gx = 1.f - fx, fy = a.yf[e], gy = 1.f - fy;
-            float r0 = res[0][0] * gx + res[0][1] * fx;
-            float r1 = res[1][0] * gx + res[1][1] * fx;
-            out = r0 * gy + r1 * fy;
-        }
-        dst[(size_t)e * a.d.pitch + d] = out;
     }
+    __syncthreads();
+
+    // row pass, only at the source columns the resize reads
+    const int ncol = IDENT ? tw_ : tw_ * 2;
+    for (int slot = lane; slot < ncol; slot += 32) {
+        int xl; // local column of tap 0
+        if (IDENT) xl = slot;
+        else xl = min(a.xi[d0 + (slot >> 1)] + (slot & 1), W - 1) - c - xs_lo;
+        if (K == 3) {
+            const float k0 = ktab[0], k1 = ktab[1];
+            for (int r = warp; r < SH; r += 8) {
+                const float *p = tile + r * SWp + xl;
+                rp[r * NC + slot] = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+            }
+        } else {
+            for (int r = warp; r < SH; r += 8) {
+                const float *p = tile + r * SWp + xl;
+                float o = p[0] * ktab[0];
+                for (int j = 1; j < K; j++) o = fmaf(p[j], ktab[j], o);
+                rp[r * NC + slot] = o;
+            }
+        }
+    }
+    __syncthreads();
+
+    // column pass at the source rows the resize reads, then the bilinear blend (A.2b)
+    float *dst = a.dst + (size_t)blockIdx.z * a.d.plane;
+    for (int ty = warp; ty < th_; ty += 8) {
+        const int e = e0 + ty;
+        const int y0 = a.yi[e], y1 = min(y0 + 1, H - 1);
+        const float fy = IDENT ? 0.f : a.yf[e];
+        for (int tx = lane; tx < tw_; tx += 32) {
+            const int d = d0 + tx;
+            float res[2][2];
+#pragma unroll
+            for (int yy = 0; yy < (IDENT ? 1 : 2); yy++) {
+                const float *col = rp + ((yy ? y1 : y0) - ys_lo) * NC + (IDENT ? tx : tx * 2);
+#pragma unroll
+                for (int xx = 0; xx < (IDENT ? 1 : 2); xx++) {
+                    const float *q = col + xx;
+                    float o;
+                    if (K == 3) {
+                        o = fmaf(q[-NC] + q[NC], ktab[0], q[0] * ktab[1]);
+                    } else {
+                        o = q[0] * ktab[c];
+                        for (int j = 1; j <= c; j++) o = fmaf(q[-j * NC] + q[j * NC], ktab[c + j], o);
+                    }
+                    res[yy][xx] = o;
+                }
+            }
+            float out;
+            if (IDENT) {
+                out = res[0][0];
+            } else {
+                const float fx = a.xf[d], gx = 1.f - fx, gy = 1.f - fy;
+                const float r0 = res[0][0] * gx + res[0][1] * fx;
+                const float r1 = res[1][0] * gx + res[1][1] * fx;
+                out = r0 * gy + r1 * fy;
+            }
+            dst[(size_t)e * a.d.pitch + d] = out;
+        }
+    }
+}
+
+size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity)
+{
+    return sizeof(float) * ((size_t)smem_h * (smem_w | 1) + (size_t)smem_h * (identity ? tile_w : tile_w * 2) + ksize);
 }
 
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a)
 {
-    int SWp = (a.smem_w + 3) & ~3;
-    int NC = a.identity ? a.tile_w : a.tile_w * 2;
-    size_t smem = (((size_t)a.smem_h * SWp + 15) & ~(size_t)15) + sizeof(float) * ((size_t)a.smem_h * NC + a.ksize);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(level_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = level_image_smem_bytes(a.smem_w, a.smem_h, a.tile_w, a.ksize, a.identity);
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[a.identity ? 1 : 0]) {
+        cudaError_t e = a.identity ? cudaFuncSetAttribute(level_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(level_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[a.identity ? 1 : 0] = smem;
     }
     dim3 grid((a.d.w + a.tile_w - 1) / a.tile_w, (a.d.h + a.tile_h - 1) / a.tile_h, a.nimg);
-    level_image_kernel<<<grid, 256, smem, s>>>(a);
+    if (a.identity) level_image_kernel<true><<<grid, 256, smem, s>>>(a);
+    else level_image_kernel<false><<<grid, 256, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -172,8 +206,8 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float *__restrict__ 
         for (int k = 1; k <= n; k++) {
             float a0 = p0[k], m0 = p0[-k], a1 = p1[k], m1 = p1[-k], a2 = p2[k], m2 = p2[-k];
             double tg = (double)(a0 + m0);
-            b1 = b1 + tg * (double)t.g[k];
-            b4 = b4 + tg * (double)t.xxg[k];
+            b1 = b1 + tg * t.gd[k];
+            b4 = b4 + tg * t.xxgd[k];
             b2 = b2 + (double)((a0 - m0) * t.xg[k]);
             b3 = b3 + (double)((a1 + m1) * t.g[k]);
             b6 = b6 + (double)((a1 - m1) * t.xg[k]);
@@ -188,8 +222,89 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float *__restrict__ 
     }
 }
 
+// K2 fast path (polyN = 7 or 5): tile 96 x 16, 256 threads.
+//   phase V: thread = (column, 8-row group): 8 + 2N inputs in registers, (r0, r1, r2) for 8 rows -> shared [3][16][112]
+//   phase H: lane = x (conflict-free LDS, coalesced stores), taps unrolled, double accumulators exactly as App. A.3.
+// The F2F.F64.F32 conversions (3 + 5N per pixel) run on the XU pipe at 16 lanes/clk/SM and bound this kernel.
+constexpr int PF_TW = 96, PF_TH = 16, PF_VW = 112, PF_RV = 8;
+
+template <int N>
+__global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restrict__ I, float *__restrict__ R, LevelDims d, PolyTables t)
+{
+    __shared__ float sm[3][PF_TH * PF_VW];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PF_TW, y0 = blockIdx.y * PF_TH;
+    const float *img = I + (size_t)blockIdx.z * d.plane;
+    const int w = d.w, h = d.h, pitch = d.pitch;
+    const bool interior = (y0 - N >= 0) && (y0 + PF_TH + N - 1 <= h - 1); // block-uniform
+
+    if (tid < 2 * PF_VW) {
+        const int g = tid / PF_VW, j = tid - g * PF_VW;
+        const int gx = clampi(x0 - 8 + j, 0, w - 1);
+        const int ybase = y0 + g * PF_RV - N;
+        float in[PF_RV + 2 * N];
+        if (interior) {
+            const float *p = img + (size_t)ybase * pitch + gx;
+#pragma unroll
+            for (int r = 0; r < PF_RV + 2 * N; r++) in[r] = __ldg(p + (size_t)r * pitch);
+        } else {
+#pragma unroll
+            for (int r = 0; r < PF_RV + 2 * N; r++) in[r] = __ldg(img + (size_t)clampi(ybase + r, 0, h - 1) * pitch + gx);
+        }
+#pragma unroll
+        for (int o = 0; o < PF_RV; o++) {
+            float r0 = in[o + N] * t.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                float up = in[o + N - k], dn = in[o + N + k];
+                float p = up + dn, q = dn - up;
+                r0 = r0 + t.g[k] * p;
+                r1 = r1 + t.xg[k] * q;
+                r2 = r2 + t.xxg[k] * p;
+            }
+            const int si = (g * PF_RV + o) * PF_VW + j;
+            sm[0][si] = r0; sm[1][si] = r1; sm[2][si] = r2;
+        }
+    }
+    __syncthreads();
+
+    float *out = R + (size_t)blockIdx.z * 5 * d.plane;
+    const float g0 = t.g[0];
+#pragma unroll 2
+    for (int i = tid; i < PF_TW * PF_TH; i += 256) {
+        const int row = i / PF_TW, col = i - row * PF_TW;
+        const int gx = x0 + col, gy = y0 + row;
+        if (gx >= w || gy >= h) continue;
+        const float *p0 = &sm[0][row * PF_VW + col + 8], *p1 = &sm[1][row * PF_VW + col + 8], *p2 = &sm[2][row * PF_VW + col + 8];
+        double b1 = (double)(p0[0] * g0), b2 = 0, b3 = (double)(p1[0] * g0), b4 = 0, b5 = (double)(p2[0] * g0), b6 = 0;
+#pragma unroll
+        for (int k = 1; k <= N; k++) {
+            const float a0 = p0[k], m0 = p0[-k], a1 = p1[k], m1 = p1[-k], a2 = p2[k], m2 = p2[-k];
+            const double tg = (double)(a0 + m0);
+            b1 = b1 + tg * t.gd[k];
+            b4 = b4 + tg * t.xxgd[k];
+            b2 = b2 + (double)((a0 - m0) * t.xg[k]);
+            b3 = b3 + (double)((a1 + m1) * t.g[k]);
+            b6 = b6 + (double)((a1 - m1) * t.xg[k]);
+            b5 = b5 + (double)((a2 + m2) * t.g[k]);
+        }
+        const size_t o = (size_t)gy * pitch + gx;
+        out[o] = (float)(b3 * t.ig11);
+        out[o + d.plane] = (float)(b2 * t.ig11);
+        out[o + 2 * d.plane] = (float)(b1 * t.ig03 + b5 * t.ig33);
+        out[o + 3 * d.plane] = (float)(b1 * t.ig03 + b4 * t.ig33);
+        out[o + 4 * d.plane] = (float)(b6 * t.ig55);
+    }
+}
+
 cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t)
 {
+    if (t.n == 7 || t.n == 5) {
+        dim3 grid((d.w + PF_TW - 1) / PF_TW, (d.h + PF_TH - 1) / PF_TH, nimg);
+        if (t.n == 7) polyexp_fast_kernel<7><<<grid, 256, 0, s>>>(I, R, d, t);
+        else polyexp_fast_kernel<5><<<grid, 256, 0, s>>>(I, R, d, t);
+        return cudaGetLastError();
+    }
     dim3 grid((d.w + PE_TW - 1) / PE_TW, (d.h + PE_TH - 1) / PE_TH, nimg);
     size_t smem = sizeof(float) * 3 * PE_TH * (PE_TW + 2 * t.n);
     polyexp_kernel<<<grid, 256, smem, s>>>(I, R, d, t);
@@ -378,6 +493,39 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
 constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_RV = 16;
 constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
 
+template <int MR, bool FMA, bool INTERIOR>
+__device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, float *__restrict__ Vb, const WinTaps &t, int tid, int x0,
+                                              int y0, int w, int h, int pitch, size_t plane)
+{
+    const int j = tid & (GK_VW - 1), g = tid >> 7;
+    const int gx = clampi(x0 - 16 + j, 0, w - 1);
+    const int ybase = y0 + g * GK_RV - MR;
+#pragma unroll 1
+    for (int c = 0; c < 5; c++) {
+        const float *Mc = Min + c * plane + gx;
+        float in[GK_RV + 2 * MR];
+        if (INTERIOR) {
+            const float *p = Mc + (size_t)ybase * pitch;
+#pragma unroll
+            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(p + (size_t)r * pitch);
+        } else {
+#pragma unroll
+            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(Mc + (size_t)clampi(ybase + r, 0, h - 1) * pitch);
+        }
+        float *dst = Vb + (c * GK_TH + g * GK_RV) * GK_VP + j;
+#pragma unroll
+        for (int o = 0; o < GK_RV; o++) {
+            float v = in[o + MR] * t.k[0];
+#pragma unroll
+            for (int i = 1; i <= MR; i++) {
+                if (FMA) v = fmaf(in[o + MR + i] + in[o + MR - i], t.k[i], v);
+                else v = v + (in[o + MR + i] + in[o + MR - i]) * t.k[i];
+            }
+            dst[o * GK_VP] = v;
+        }
+    }
+}
+
 template <int MR, bool FMA>
 __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps t)
 {
@@ -390,37 +538,21 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     const size_t plane = a.d.plane;
     const float *Min = a.Min + (size_t)b * 5 * plane;
 
-    // ---- phase V ----
-    {
-        const int j = tid & (GK_VW - 1), g = tid >> 7;
-        const int gx = clampi(x0 - 16 + j, 0, w - 1);
-        const int ybase = y0 + g * GK_RV - MR;
-        const bool interior = ybase >= 0 && ybase + GK_RV + 2 * MR - 1 <= h - 1;
-#pragma unroll 1
-        for (int c = 0; c < 5; c++) {
-            const float *Mc = Min + c * plane + gx;
-            float in[GK_RV + 2 * MR];
-            if (interior) {
-                const float *p = Mc + (size_t)ybase * pitch;
-#pragma unroll
-                for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(p + (size_t)r * pitch);
-            } else {
-#pragma unroll
-                for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(Mc + (size_t)clampi(ybase + r, 0, h - 1) * pitch);
-            }
-            float *dst = Vb + (c * GK_TH + g * GK_RV) * GK_VP + j;
-#pragma unroll
-            for (int o = 0; o < GK_RV; o++) {
-                float v = in[o + MR] * t.k[0];
-#pragma unroll
-                for (int i = 1; i <= MR; i++) {
-                    if (FMA) v = fmaf(in[o + MR + i] + in[o + MR - i], t.k[i], v);
-                    else v = v + (in[o + MR + i] + in[o + MR - i]) * t.k[i];
-                }
-                dst[o * GK_VP] = v;
-            }
+    // The epilogue's R0 / R1 reads are latency-bound: pull the tile's lines into L2 while the blur runs.
+    if (!a.last) {
+        const float *Rb = a.R + (size_t)b * 10 * plane;
+        for (int i = tid; i < 10 * GK_TH * 3; i += 256) {
+            const int pl = i / (GK_TH * 3), rem = i - pl * (GK_TH * 3), row = rem / 3, seg = rem - row * 3;
+            const int y = min(y0 + row, h - 1), x = min(x0 + seg * 32, w - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + pl * plane + (size_t)y * pitch + x));
         }
     }
+
+    // ---- phase V ----
+    if ((y0 - MR >= 0) && (y0 + GK_TH + MR - 1 <= h - 1)) // block-uniform: no row clamping needed
+        gauss_v_phase<MR, FMA, true>(Min, Vb, t, tid, x0, y0, w, h, pitch, plane);
+    else
+        gauss_v_phase<MR, FMA, false>(Min, Vb, t, tid, x0, y0, w, h, pitch, plane);
     __syncthreads();
 
     // ---- phase H + solve ----
@@ -466,7 +598,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
 
     // ---- phase U: coalesced epilogue ----
     const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
-#pragma unroll 1
+#pragma unroll 2
     for (int i = tid; i < GK_TW * GK_TH; i += 256) {
         const int row = i / GK_TW, col = i - row * GK_TW;
         const int x = x0 + col, y = y0 + row;

@@ -16,6 +16,7 @@ constexpr int kMaxWinRadius = 32; // winSize/2
 
 struct PolyTables {
     float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
+    double gd[kMaxPolyN + 1], xxgd[kMaxPolyN + 1]; // (double)g[k], (double)xxg[k]: no conversions in the tap loop
     double ig11, ig03, ig33, ig55;
     int n;
 };
@@ -43,8 +44,10 @@ struct LevelImageArgs {
     int tile_w, tile_h; // output tile
     int smem_w, smem_h; // source tile bound (before clamping)
     int identity;       // w == W && h == H
+    int small;          // ksize/2 >= min(W, H): multi-bounce reflect path
 };
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a);
+size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity);
 
 // K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
 cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t);
