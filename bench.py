@@ -170,18 +170,8 @@ def main():
         run_reference(args, rank)
         return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_
-        torch.cuda.set_device(local_rank)
-        try:
-            dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        except Exception:
-            dist_.init_process_group("gloo")
-        dist = dist_
-
     import tidalwave_b200 as tw
+    dist = tw.dist.Dist()  # nccl when launched by torch.distributed.run with N > 1; no-op at N = 1
     lib = tw.load()
     B = args.batch
     pairs = make_pool(B)  # every rank: same seeded pool, its own copy (weak scaling: B pairs per step per GPU)
@@ -224,9 +214,7 @@ def main():
     check(lib.tw_batch_fetch(of.ctx, B, vec, cap, res), "fetch")
     statuses = [res[i].status for i in range(B)]
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    barrier = dist.barrier
 
     of.profile(True)
     l0 = of.launch_count()
@@ -243,13 +231,8 @@ def main():
     launches = of.launch_count() - l0
     prof = of.profile_read()
     of.profile(False)
-    elapsed_ms = float(ms.value)
-    if dist is not None:
-        import torch
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    elapsed_ms = dist.reduce_max(float(ms.value))  # device time of the slowest rank
+    value = tw.dist.whole_job_throughput(B * args.steps, world, elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel family ----
     peak, peak_src = measured_peaks()
@@ -293,12 +276,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         nv = run_pool(n_req)
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            import torch
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = dist.reduce_max(time.perf_counter() - t0)
         lib.tw_pool_destroy(pool)
         e2e = {"value": world * n_req / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * npx * B,
                "d2h_bytes_per_step": int(4 * B + 24 * nv * B / n_req), "pairs": n_req,
@@ -324,9 +302,7 @@ def main():
                 "statuses": statuses}
         print(json.dumps(line), flush=True)
     of.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    dist.close()
 
 
 if __name__ == "__main__":

@@ -16,9 +16,9 @@ using namespace tw;
 
 namespace {
 
-enum Family { F_LEVEL = 0, F_POLY, F_FIRST, F_GITER, F_GLAST, F_BVSUM, F_BITER, F_BLAST, F_SAMPLE, F_COUNT };
+enum Family { F_LEVEL = 0, F_POLY, F_FIRST, F_GITER, F_GLAST, F_BVSUM, F_BITER, F_BLAST, F_BUPD, F_SAMPLE, F_COUNT };
 const char *kFamilyNames[F_COUNT] = {"level_image", "polyexp", "first_update", "gauss_iter", "gauss_last",
-                                     "box_vsum", "box_iter", "box_last", "sample"};
+                                     "box_vsum", "box_hscan", "box_hscan_last", "box_update", "sample"};
 
 struct Scale {
     int k, ksize;
@@ -340,7 +340,7 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
             s.I = I; s.R = R; s.M0 = M0; s.M1 = M1;
         }
     }
-    if (p.flags == 0 && !dev_alloc(ctx, &pl.V, (size_t)B * 5 * fine.d.plane)) return false;
+    if (p.flags == 0 && !dev_alloc(ctx, &pl.V, (size_t)B * 5 * (size_t)(fine.d.w + 32) * (size_t)(fine.d.h + 32))) return false;
     pl.valid = true;
     return true;
 }
@@ -441,7 +441,12 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
             } else {
                 LAUNCH(F_BVSUM, 0.0, launch_box_vsum(ctx->stream, Min, pl.V, s.d, n, p.winSize / 2));
-                LAUNCH(ia.last ? F_BLAST : F_BITER, bytes, launch_box_iter(ctx->stream, pl.V, ia, p.winSize / 2, p.winSize));
+                LAUNCH(ia.last ? F_BLAST : F_BITER, bytes, launch_box_hscan(ctx->stream, pl.V, s.flow, s.d, n, p.winSize / 2, p.winSize));
+                if (!ia.last) {
+                    FirstUpdateArgs ua{};
+                    ua.flow_in = s.flow; ua.R = s.R; ua.M = Mout; ua.d = s.d; ua.batch = n; ua.inv_scale = 1.f;
+                    LAUNCH(F_BUPD, 0.0, launch_first_update(ctx->stream, ua));
+                }
             }
             if (!ia.last) std::swap(Min, Mout);
         }

@@ -270,30 +270,51 @@ __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restri
 
     float *out = R + (size_t)blockIdx.z * 5 * d.plane;
     const float g0 = t.g[0];
-#pragma unroll 2
-    for (int i = tid; i < PF_TW * PF_TH; i += 256) {
-        const int row = i / PF_TW, col = i - row * PF_TW;
+    // 2 adjacent pixels per thread: 2N+2 floats per plane as 8-byte shared loads (lane stride 8 B: conflict-free)
+#pragma unroll 1
+    for (int i = tid; i < (PF_TW / 2) * PF_TH; i += 256) {
+        const int row = i / (PF_TW / 2), col = (i - row * (PF_TW / 2)) * 2;
         const int gx = x0 + col, gy = y0 + row;
         if (gx >= w || gy >= h) continue;
-        const float *p0 = &sm[0][row * PF_VW + col + 8], *p1 = &sm[1][row * PF_VW + col + 8], *p2 = &sm[2][row * PF_VW + col + 8];
-        double b1 = (double)(p0[0] * g0), b2 = 0, b3 = (double)(p1[0] * g0), b4 = 0, b5 = (double)(p2[0] * g0), b6 = 0;
+        // taps of pixel col are smem columns col+8-N .. col+8+N; col is even, so col+8-NE (NE = N rounded up to even) is 8B-aligned
+        constexpr int NE = (N + 1) & ~1, NF = 2 * NE + 2;
+        float v[3][NF];
 #pragma unroll
-        for (int k = 1; k <= N; k++) {
-            const float a0 = p0[k], m0 = p0[-k], a1 = p1[k], m1 = p1[-k], a2 = p2[k], m2 = p2[-k];
-            const double tg = (double)(a0 + m0);
-            b1 = b1 + tg * t.gd[k];
-            b4 = b4 + tg * t.xxgd[k];
-            b2 = b2 + (double)((a0 - m0) * t.xg[k]);
-            b3 = b3 + (double)((a1 + m1) * t.g[k]);
-            b6 = b6 + (double)((a1 - m1) * t.xg[k]);
-            b5 = b5 + (double)((a2 + m2) * t.g[k]);
+        for (int pl = 0; pl < 3; pl++) {
+            const float2 *src = reinterpret_cast<const float2 *>(&sm[pl][row * PF_VW + col + 8 - NE]);
+#pragma unroll
+            for (int q = 0; q < NF / 2; q++) { float2 u = src[q]; v[pl][2 * q] = u.x; v[pl][2 * q + 1] = u.y; }
+        }
+        float res[2][5];
+#pragma unroll
+        for (int px = 0; px < 2; px++) {
+            const int ctr = NE + px;
+            double b1 = (double)(v[0][ctr] * g0), b2 = 0, b3 = (double)(v[1][ctr] * g0), b4 = 0, b5 = (double)(v[2][ctr] * g0), b6 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                const float a0 = v[0][ctr + k], m0 = v[0][ctr - k], a1 = v[1][ctr + k], m1 = v[1][ctr - k], a2 = v[2][ctr + k], m2 = v[2][ctr - k];
+                const double tg = (double)(a0 + m0);
+                b1 = b1 + tg * t.gd[k];
+                b4 = b4 + tg * t.xxgd[k];
+                b2 = b2 + (double)((a0 - m0) * t.xg[k]);
+                b3 = b3 + (double)((a1 + m1) * t.g[k]);
+                b6 = b6 + (double)((a1 - m1) * t.xg[k]);
+                b5 = b5 + (double)((a2 + m2) * t.g[k]);
+            }
+            res[px][0] = (float)(b3 * t.ig11);
+            res[px][1] = (float)(b2 * t.ig11);
+            res[px][2] = (float)(b1 * t.ig03 + b5 * t.ig33);
+            res[px][3] = (float)(b1 * t.ig03 + b4 * t.ig33);
+            res[px][4] = (float)(b6 * t.ig55);
         }
         const size_t o = (size_t)gy * pitch + gx;
-        out[o] = (float)(b3 * t.ig11);
-        out[o + d.plane] = (float)(b2 * t.ig11);
-        out[o + 2 * d.plane] = (float)(b1 * t.ig03 + b5 * t.ig33);
-        out[o + 3 * d.plane] = (float)(b1 * t.ig03 + b4 * t.ig33);
-        out[o + 4 * d.plane] = (float)(b6 * t.ig55);
+        if (gx + 1 < w) {
+#pragma unroll
+            for (int c = 0; c < 5; c++) *reinterpret_cast<float2 *>(out + o + c * d.plane) = make_float2(res[0][c], res[1][c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; c++) out[o + c * d.plane] = res[0][c];
+        }
     }
 }
 
@@ -317,35 +338,58 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 // border damping {0.14, 0.14, 0.4472, 0.4472, 0.4472} indexed by the distance to the edge (App. A.4)
 __device__ __forceinline__ float border_tab(int i) { return i < 2 ? 0.14f : 0.4472f; }
 
-__device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane,
-                                                   int pitch, int w, int h, int x, int y, float dx, float dy, float m[5])
+// The epilogues are latency-bound, so the 25 loads of a pixel are issued first (upd_load) for several pixels
+// and consumed afterwards (upd_compute).
+struct UpdLoad {
+    float q[5];    // R0 at (x, y)
+    float p[5][4]; // R1 at (x1, y1), (x1+1, y1), (x1, y1+1), (x1+1, y1+1)
+    float fx, fy;
+    bool inside;
+};
+
+__device__ __forceinline__ void upd_load(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane, int pitch, int w,
+                                         int h, int x, int y, float dx, float dy, UpdLoad &L)
 {
     const size_t o = (size_t)y * pitch + x;
     float fx = (float)x + dx, fy = (float)y + dy;
-    int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-    fx = fx - (float)x1;
-    fy = fy - (float)y1;
-    float r2, r3, r4, r5, r6;
-    const float q0 = R0[o], q1 = R0[o + plane], q2 = R0[o + 2 * plane], q3 = R0[o + 3 * plane], q4 = R0[o + 4 * plane];
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+    L.fx = fx - (float)x1;
+    L.fy = fy - (float)y1;
+    L.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+#pragma unroll
+    for (int c = 0; c < 5; c++) L.q[c] = __ldg(R0 + o + c * plane);
+    if (L.inside) {
         const float *p = R1 + (size_t)y1 * pitch + x1;
-        r2 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += plane;
-        r3 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += plane;
-        r4 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += plane;
-        r5 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += plane;
-        r6 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1];
-        r4 = (q2 + r4) * 0.5f;
-        r5 = (q3 + r5) * 0.5f;
-        r6 = (q4 + r6) * 0.25f;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            L.p[c][0] = __ldg(p); L.p[c][1] = __ldg(p + 1); L.p[c][2] = __ldg(p + pitch); L.p[c][3] = __ldg(p + pitch + 1);
+            p += plane;
+        }
+    }
+}
+
+__device__ __forceinline__ void upd_compute(const UpdLoad &L, int w, int h, int x, int y, float dx, float dy, float m[5])
+{
+    float r2, r3, r4, r5, r6;
+    if (L.inside) {
+        const float fx = L.fx, fy = L.fy;
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        r2 = a00 * L.p[0][0] + a01 * L.p[0][1] + a10 * L.p[0][2] + a11 * L.p[0][3];
+        r3 = a00 * L.p[1][0] + a01 * L.p[1][1] + a10 * L.p[1][2] + a11 * L.p[1][3];
+        r4 = a00 * L.p[2][0] + a01 * L.p[2][1] + a10 * L.p[2][2] + a11 * L.p[2][3];
+        r5 = a00 * L.p[3][0] + a01 * L.p[3][1] + a10 * L.p[3][2] + a11 * L.p[3][3];
+        r6 = a00 * L.p[4][0] + a01 * L.p[4][1] + a10 * L.p[4][2] + a11 * L.p[4][3];
+        r4 = (L.q[2] + r4) * 0.5f;
+        r5 = (L.q[3] + r5) * 0.5f;
+        r6 = (L.q[4] + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = q2;
-        r5 = q3;
-        r6 = q4 * 0.5f;
+        r4 = L.q[2];
+        r5 = L.q[3];
+        r6 = L.q[4] * 0.5f;
     }
-    r2 = (q0 - r2) * 0.5f;
-    r3 = (q1 - r3) * 0.5f;
+    r2 = (L.q[0] - r2) * 0.5f;
+    r3 = (L.q[1] - r3) * 0.5f;
     r2 = r2 + (r4 * dy + r6 * dx);
     r3 = r3 + (r6 * dy + r5 * dx);
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
@@ -358,6 +402,14 @@ __device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0,
     m[2] = r5 * r5 + r6 * r6;
     m[3] = r4 * r2 + r6 * r3;
     m[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane,
+                                                   int pitch, int w, int h, int x, int y, float dx, float dy, float m[5])
+{
+    UpdLoad L;
+    upd_load(R0, R1, plane, pitch, w, h, x, y, dx, dy, L);
+    upd_compute(L, w, h, x, y, dx, dy, m);
 }
 
 __device__ __forceinline__ void solve2x2(float g11f, float g12f, float g22f, float h1f, float h2f, float &fx, float &fy)
@@ -379,41 +431,64 @@ __device__ __forceinline__ void solve2x2d(double g11, double g12, double g22, do
 // K3  flow initialisation for a scale (zero, or bilinear upsample of the coarser flow * 1/pyrScale,
 //     App. A.1 / A.2b) fused with the first update-matrices (A.4).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void upsample_flow_px(const FirstUpdateArgs &a, int b, int x, int y, float &dx, float &dy)
+{
+    dx = 0.f; dy = 0.f;
+    if (a.flow_in) { // same-size flow (box window: the solve ran in its own kernel)
+        const float *f = a.flow_in + (size_t)b * 2 * a.d.plane + (size_t)y * a.d.pitch + x;
+        dx = __ldg(f); dy = __ldg(f + a.d.plane);
+        return;
+    }
+    if (!a.coarse) return;
+    const float *cf = a.coarse + (size_t)b * 2 * a.cd.plane;
+    const int x0 = __ldg(a.xi + x), x1 = min(x0 + 1, a.cd.w - 1), y0 = __ldg(a.yi + y), y1 = min(y0 + 1, a.cd.h - 1);
+    const float fx = __ldg(a.xf + x), gx = 1.f - fx, fy = __ldg(a.yf + y), gy = 1.f - fy;
+    const float *r0 = cf + (size_t)y0 * a.cd.pitch, *r1 = cf + (size_t)y1 * a.cd.pitch;
+    const float a00 = __ldg(r0 + x0), a01 = __ldg(r0 + x1), a10 = __ldg(r1 + x0), a11 = __ldg(r1 + x1);
+    r0 += a.cd.plane; r1 += a.cd.plane;
+    const float b00 = __ldg(r0 + x0), b01 = __ldg(r0 + x1), b10 = __ldg(r1 + x0), b11 = __ldg(r1 + x1);
+    float t0 = a00 * gx + a01 * fx, t1 = a10 * gx + a11 * fx;
+    dx = (t0 * gy + t1 * fy) * a.inv_scale;
+    t0 = b00 * gx + b01 * fx; t1 = b10 * gx + b11 * fx;
+    dy = (t0 * gy + t1 * fy) * a.inv_scale;
+}
+
 __global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= a.d.w || y >= a.d.h) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, ya = blockIdx.y * 16 + threadIdx.y, yb = ya + 8;
+    if (x >= a.d.w || ya >= a.d.h) return;
+    const bool hasb = yb < a.d.h;
     const int b = blockIdx.z;
-    float dx = 0.f, dy = 0.f;
-    if (a.coarse) {
-        const float *cf = a.coarse + (size_t)b * 2 * a.cd.plane;
-        int x0 = a.xi[x], x1 = min(x0 + 1, a.cd.w - 1), y0 = a.yi[y], y1 = min(y0 + 1, a.cd.h - 1);
-        float fx = a.xf[x], gx = 1.f - fx, fy = a.yf[y], gy = 1.f - fy;
-        const float *r0 = cf + (size_t)y0 * a.cd.pitch, *r1 = cf + (size_t)y1 * a.cd.pitch;
-        float t0 = r0[x0] * gx + r0[x1] * fx, t1 = r1[x0] * gx + r1[x1] * fx;
-        dx = (t0 * gy + t1 * fy) * a.inv_scale;
-        r0 += a.cd.plane; r1 += a.cd.plane;
-        t0 = r0[x0] * gx + r0[x1] * fx; t1 = r1[x0] * gx + r1[x1] * fx;
-        dy = (t0 * gy + t1 * fy) * a.inv_scale;
-    }
-    const size_t o = (size_t)y * a.d.pitch + x;
+    float dxa, dya, dxb = 0.f, dyb = 0.f;
+    upsample_flow_px(a, b, x, ya, dxa, dya);
+    if (hasb) upsample_flow_px(a, b, x, yb, dxb, dyb);
+    const size_t oa = (size_t)ya * a.d.pitch + x, ob = (size_t)yb * a.d.pitch + x;
     if (a.flow_out) {
         float *f = a.flow_out + (size_t)b * 2 * a.d.plane;
-        f[o] = dx; f[o + a.d.plane] = dy;
+        f[oa] = dxa; f[oa + a.d.plane] = dya;
+        if (hasb) { f[ob] = dxb; f[ob + a.d.plane] = dyb; }
     }
     if (a.M) {
-        float m[5];
         const float *R0 = a.R + (size_t)b * 10 * a.d.plane, *R1 = R0 + 5 * a.d.plane;
-        update_matrices_px(R0, R1, a.d.plane, a.d.pitch, a.d.w, a.d.h, x, y, dx, dy, m);
+        UpdLoad La, Lb;
+        upd_load(R0, R1, a.d.plane, a.d.pitch, a.d.w, a.d.h, x, ya, dxa, dya, La);
+        if (hasb) upd_load(R0, R1, a.d.plane, a.d.pitch, a.d.w, a.d.h, x, yb, dxb, dyb, Lb);
         float *M = a.M + (size_t)b * 5 * a.d.plane;
+        float m[5];
+        upd_compute(La, a.d.w, a.d.h, x, ya, dxa, dya, m);
 #pragma unroll
-        for (int c = 0; c < 5; c++) M[o + c * a.d.plane] = m[c];
+        for (int c = 0; c < 5; c++) M[oa + c * a.d.plane] = m[c];
+        if (hasb) {
+            upd_compute(Lb, a.d.w, a.d.h, x, yb, dxb, dyb, m);
+#pragma unroll
+            for (int c = 0; c < 5; c++) M[ob + c * a.d.plane] = m[c];
+        }
     }
 }
 
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a)
 {
-    dim3 grid((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.batch);
+    dim3 grid((a.d.w + 31) / 32, (a.d.h + 15) / 16, a.batch);
     first_update_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
     return cudaGetLastError();
 }
@@ -597,21 +672,43 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     __syncthreads();
 
     // ---- phase U: coalesced epilogue ----
+    if (a.last) {
+        float *f = a.flow + (size_t)b * 2 * plane;
+#pragma unroll 4
+        for (int i = tid; i < GK_TW * GK_TH; i += 256) {
+            const int row = i / GK_TW, col = i - row * GK_TW;
+            const int x = x0 + col, y = y0 + row;
+            if (x >= w || y >= h) continue;
+            const size_t o = (size_t)y * pitch + x;
+            f[o] = Fb[row * GK_FP + col];
+            f[o + plane] = Fb[(GK_TH + row) * GK_FP + col];
+        }
+        return;
+    }
     const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
-#pragma unroll 2
-    for (int i = tid; i < GK_TW * GK_TH; i += 256) {
-        const int row = i / GK_TW, col = i - row * GK_TW;
-        const int x = x0 + col, y = y0 + row;
-        if (x >= w || y >= h) continue;
-        const float fx = Fb[row * GK_FP + col], fy = Fb[(GK_TH + row) * GK_FP + col];
-        const size_t o = (size_t)y * pitch + x;
-        if (a.last) {
-            float *f = a.flow + (size_t)b * 2 * plane;
-            f[o] = fx; f[o + plane] = fy;
-        } else {
+    float *M = a.Mout + (size_t)b * 5 * plane;
+    // 12 pixels per thread, in 4 rounds of 3: all loads of a round are in flight together
+#pragma unroll 1
+    for (int rnd = 0; rnd < 4; rnd++) {
+        UpdLoad L[3];
+        float fx[3], fy[3];
+        int xs[3], ys[3];
+        bool ok[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int i = tid + (rnd * 3 + u) * 256;
+            const int row = i / GK_TW, col = i - row * GK_TW;
+            xs[u] = x0 + col; ys[u] = y0 + row;
+            ok[u] = xs[u] < w && ys[u] < h;
+            fx[u] = Fb[row * GK_FP + col]; fy[u] = Fb[(GK_TH + row) * GK_FP + col];
+            if (ok[u]) upd_load(R0, R1, plane, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            if (!ok[u]) continue;
             float mm[5];
-            update_matrices_px(R0, R1, plane, pitch, w, h, x, y, fx, fy, mm);
-            float *M = a.Mout + (size_t)b * 5 * plane;
+            upd_compute(L[u], w, h, xs[u], ys[u], fx[u], fy[u], mm);
+            const size_t o = (size_t)ys[u] * pitch + xs[u];
 #pragma unroll
             for (int c = 0; c < 5; c++) M[o + c * plane] = mm[c];
         }
@@ -643,68 +740,94 @@ cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &
 }
 
 // ------------------------------------------------------------------------------------------------
-// Box window (flags == 0), App. A.6.
-//   box_vsum: one thread per (column, plane) walks down the column keeping the oracle's running sum:
-//             vs += double(float(M[y+m] - M[y-m-1])) -- the float difference is part of the answer.
-//   box_iter: horizontal window of 2m+1 doubles (replicate border), * 1/winSize^2, solve, update/flow.
+// Box window (flags == 0), App. A.6.  Both running sums are evaluated in the oracle's order, because the
+// regularised 2x2 solve amplifies even 1e-16-relative re-association differences on screenshot content
+// (measured: a direct window sum moved config 4 by up to 0.12 px on 3e-5 of the pixels).
+//   box_vsum : one thread per (column, plane) walks DOWN the column:  vs += double(float(M[y+m] - M[y-m-1]))
+//              (the float difference is part of the answer); V is stored transposed, VT[plane][x][y].
+//   box_hscan: one lane per row walks ALONG the row: g += V[x+m] - V[x-m-1] in double (coalesced reads of VT),
+//              b = g / winSize^2, 2x2 solve, flow staged through a 32x32 shared tile for coalesced writes.
+//   The next update-matrices then runs as first_update_kernel with flow_in.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) box_vsum_kernel(const float *__restrict__ Min, double *__restrict__ V, LevelDims d, int m)
+__global__ void __launch_bounds__(128) box_vsum_kernel(const float *__restrict__ Min, double *__restrict__ VT, LevelDims d, int m,
+                                                       int pitchT, size_t planeT)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= d.w) return;
     const float *M = Min + (size_t)blockIdx.y * d.plane + x;
-    double *v = V + (size_t)blockIdx.y * d.plane + x;
+    double *v = VT + (size_t)blockIdx.y * planeT + (size_t)x * pitchT;
     const int h = d.h, pitch = d.pitch;
     double vs = (double)(M[0] * (float)(m + 2));
     for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * pitch];
+#pragma unroll 4
     for (int y = 0; y < h; y++) {
-        float diff = M[(size_t)min(y + m, h - 1) * pitch] - M[(size_t)max(y - m - 1, 0) * pitch];
+        float diff = __ldg(M + (size_t)min(y + m, h - 1) * pitch) - __ldg(M + (size_t)max(y - m - 1, 0) * pitch);
         vs = vs + (double)diff;
-        v[(size_t)y * pitch] = vs;
+        v[y] = vs;
     }
 }
 
-cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *V, const LevelDims &d, int batch, int m)
+cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *VT, const LevelDims &d, int batch, int m)
 {
+    const int pitchT = (d.h + 31) & ~31;
     dim3 grid((d.w + 127) / 128, batch * 5);
-    box_vsum_kernel<<<grid, 128, 0, s>>>(Min, V, d, m);
+    box_vsum_kernel<<<grid, 128, 0, s>>>(Min, VT, d, m, pitchT, (size_t)d.w * pitchT);
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) box_iter_kernel(const double *__restrict__ V, IterArgs a, int m, double scale)
+__global__ void __launch_bounds__(128) box_hscan_kernel(const double *__restrict__ VT, float *__restrict__ flow, LevelDims d, int m,
+                                                        double scale, int pitchT, size_t planeT)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch, b = blockIdx.z;
-    if (x >= w || y >= h) return;
-    const size_t plane = a.d.plane;
+    __shared__ float tile[4][2][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = (blockIdx.x * 4 + warp) * 32, b = blockIdx.y;
+    const int w = d.w, h = d.h;
+    if (y0 >= h) return;
+    const int y = min(y0 + lane, h - 1);
+    const double *V = VT + (size_t)b * 5 * planeT + y;
     double g[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) {
-        const double *row = V + ((size_t)b * 5 + c) * plane + (size_t)y * pitch;
-        double s = 0;
-        for (int j = -m; j <= m; j++) s = s + row[clampi(x + j, 0, w - 1)];
-        g[c] = s * scale;
+        const double *Vc = V + c * planeT;
+        double t = Vc[0] * (double)(m + 2);
+        for (int x = 1; x < m; x++) t = t + Vc[(size_t)min(x, w - 1) * pitchT];
+        g[c] = t;
     }
-    float fx, fy;
-    solve2x2d(g[0], g[1], g[2], g[3], g[4], fx, fy);
-    size_t o = (size_t)y * pitch + x;
-    if (a.last) {
-        float *f = a.flow + (size_t)b * 2 * plane;
-        f[o] = fx; f[o + plane] = fy;
-    } else {
-        const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
-        float mm[5];
-        update_matrices_px(R0, R1, plane, pitch, w, h, x, y, fx, fy, mm);
-        float *M = a.Mout + (size_t)b * 5 * plane;
+    float *fxp = flow + (size_t)b * 2 * d.plane, *fyp = fxp + d.plane;
+    for (int xc = 0; xc < w; xc += 32) {
+        const int n = min(32, w - xc);
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {
+            const int x = xc + i;
+            const size_t oa = (size_t)min(x + m, w - 1) * pitchT, ob = (size_t)max(x - m - 1, 0) * pitchT;
+            double bb[5];
 #pragma unroll
-        for (int c = 0; c < 5; c++) M[o + c * plane] = mm[c];
+            for (int c = 0; c < 5; c++) {
+                g[c] = g[c] + (V[c * planeT + oa] - V[c * planeT + ob]);
+                bb[c] = g[c] * scale;
+            }
+            float fx, fy;
+            solve2x2d(bb[0], bb[1], bb[2], bb[3], bb[4], fx, fy);
+            tile[warp][0][lane][i] = fx;
+            tile[warp][1][lane][i] = fy;
+        }
+        __syncwarp();
+        for (int r = 0; r < 32 && y0 + r < h; r++) {
+            if (lane < n) {
+                const size_t o = (size_t)(y0 + r) * d.pitch + xc + lane;
+                fxp[o] = tile[warp][0][r][lane];
+                fyp[o] = tile[warp][1][r][lane];
+            }
+        }
+        __syncwarp();
     }
 }
 
-cudaError_t launch_box_iter(cudaStream_t s, const double *V, const IterArgs &a, int m, int winSize)
+cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, const LevelDims &d, int batch, int m, int winSize)
 {
-    dim3 grid((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.batch);
-    box_iter_kernel<<<grid, dim3(32, 8), 0, s>>>(V, a, m, 1. / ((double)winSize * winSize));
+    const int pitchT = (d.h + 31) & ~31;
+    dim3 grid((d.h + 127) / 128, batch);
+    box_hscan_kernel<<<grid, 128, 0, s>>>(VT, flow, d, m, 1. / ((double)winSize * winSize), pitchT, (size_t)d.w * pitchT);
     return cudaGetLastError();
 }
 

@@ -54,6 +54,7 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 
 // K3: (coarse flow -> bilinear upsample * 1/pyrScale | zero) -> first update-matrices, App. A.1 + A.4.
 struct FirstUpdateArgs {
+    const float *flow_in; // [B][2] planes of THIS scale (box window path), or nullptr
     const float *coarse; // [B][2][ch][cpitch] or nullptr (coarsest scale: zero flow)
     LevelDims cd;
     const int *xi; const float *xf; const int *yi; const float *yf; // upsample tables
@@ -78,10 +79,11 @@ struct IterArgs {
     int fma; // validated relaxation: fmaf in the Gaussian tap sums (never set for the box window)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
-// Box window (flags == 0), App. A.6: vertical float-difference running sums in double (V planes), then
-// horizontal window + solve (+ update).
-cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *V, const LevelDims &d, int batch, int m);
-cudaError_t launch_box_iter(cudaStream_t s, const double *V, const IterArgs &a, int m, int winSize);
+// Box window (flags == 0), App. A.6: vertical float-difference running sums in double (VT = V transposed,
+// [B*5][w][roundup(h,32)] doubles), then the horizontal running sum + solve -> flow; the next update-matrices
+// is launch_first_update with flow_in.
+cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *VT, const LevelDims &d, int batch, int m);
+cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, const LevelDims &d, int batch, int m, int winSize);
 
 // Span sampling + threshold classification + ordered compaction, reference src/consumer.cpp:60-77.
 struct SampleArgs {
