@@ -56,7 +56,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
-    int opt_gauss_fma = 0;
+    int opt_gauss_fma = 0, opt_gauss_scalar = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -215,6 +215,7 @@ void window_taps(int winSize, WinTaps &t)
     int m = winSize / 2;
     double sigma = m * 0.3, s = 1.;
     t.m = m;
+    t.one = 1.0f;
     t.k[0] = 1.f;
     for (int i = 1; i <= m; i++) {
         float v = (float)std::exp(-i * i / (2 * sigma * sigma));
@@ -436,6 +437,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
             ia.last = (it == p.pyrIterations - 1);
             ia.fma = ctx->opt_gauss_fma;
+            ia.scalar = ctx->opt_gauss_scalar;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
             if (p.flags & 256) {
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
@@ -792,6 +794,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
 {
     if (!ctx || !name) return TW_BAD_PARAMETER;
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;
 }
@@ -827,6 +830,22 @@ int tw_debug_read(tw_ctx *ctx, const char *name, int scale, int pair, float *out
     if ((size_t)cn * s.d.w * s.d.h > (size_t)cap_floats) return -2;
     if (w) *w = s.d.w;
     if (h) *h = s.d.h;
+    if (!strcmp(name, "M")) {
+        // M is stored as two float2 planes + one float plane (tw_kernels.cu): de-interleave on the host
+        std::vector<float> tmp(5 * s.d.plane);
+        if (cudaMemcpyAsync(tmp.data(), base, sizeof(float) * 5 * s.d.plane, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return -3;
+        const size_t P = (size_t)s.d.w * s.d.h;
+        for (int y = 0; y < s.d.h; y++)
+            for (int x = 0; x < s.d.w; x++) {
+                const size_t o = (size_t)y * s.d.pitch + x, q = (size_t)y * s.d.w + x;
+                out[q] = tmp[2 * o]; out[P + q] = tmp[2 * o + 1];
+                out[2 * P + q] = tmp[2 * s.d.plane + 2 * o]; out[3 * P + q] = tmp[2 * s.d.plane + 2 * o + 1];
+                out[4 * P + q] = tmp[4 * s.d.plane + o];
+            }
+        return cn;
+    }
     for (int c = 0; c < cn; c++) {
         cudaError_t e = cudaMemcpy2DAsync(out + (size_t)c * s.d.w * s.d.h, sizeof(float) * s.d.w, base + (size_t)c * s.d.plane,
                                           sizeof(float) * s.d.pitch, sizeof(float) * s.d.w, s.d.h, cudaMemcpyDeviceToHost, ctx->stream);

@@ -338,6 +338,28 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 // border damping {0.14, 0.14, 0.4472, 0.4472, 0.4472} indexed by the distance to the edge (App. A.4)
 __device__ __forceinline__ float border_tab(int i) { return i < 2 ? 0.14f : 0.4472f; }
 
+// ------------------------------------------------------------------------------------------------
+// M layout (per pair, 5*plane floats): two float2 planes and one float plane,
+//   [0, 2*plane)        (G11, G12) as float2 [h][pitch]
+//   [2*plane, 4*plane)  (G22, h1)  as float2 [h][pitch]
+//   [4*plane, 5*plane)  h2         as float  [h][pitch]
+// so that the packed f32x2 window kernel loads both channels of a pair with ONE 8-byte load per row (the address
+// arithmetic of two separate planes cost more issue slots than the arithmetic it fed), and writers store float2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_M(float *__restrict__ Mb, size_t plane, size_t o, const float m[5])
+{
+    *reinterpret_cast<float2 *>(Mb + 2 * o) = make_float2(m[0], m[1]);
+    *reinterpret_cast<float2 *>(Mb + 2 * plane + 2 * o) = make_float2(m[2], m[3]);
+    Mb[4 * plane + o] = m[4];
+}
+// channel c of M as a strided scalar view: element (y, x) is base[(y * pitch + x) * stride]
+__device__ __forceinline__ const float *M_channel(const float *Mb, size_t plane, int c, int &stride)
+{
+    if (c < 4) { stride = 2; return Mb + (size_t)(c >> 1) * 2 * plane + (c & 1); }
+    stride = 1;
+    return Mb + 4 * plane;
+}
+
 // The epilogues are latency-bound, so the 25 loads of a pixel are issued first (upd_load) for several pixels
 // and consumed afterwards (upd_compute).
 struct UpdLoad {
@@ -476,12 +498,10 @@ __global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
         float *M = a.M + (size_t)b * 5 * a.d.plane;
         float m[5];
         upd_compute(La, a.d.w, a.d.h, x, ya, dxa, dya, m);
-#pragma unroll
-        for (int c = 0; c < 5; c++) M[oa + c * a.d.plane] = m[c];
+        store_M(M, a.d.plane, oa, m);
         if (hasb) {
             upd_compute(Lb, a.d.w, a.d.h, x, yb, dxb, dyb, m);
-#pragma unroll
-            for (int c = 0; c < 5; c++) M[ob + c * a.d.plane] = m[c];
+            store_M(M, a.d.plane, ob, m);
         }
     }
 }
@@ -511,15 +531,16 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     float acc[5][4];
     for (int c = 0; c < 5; c++) {
-        const float *Mc = Min + c * plane;
+        int es;
+        const float *Mc = M_channel(Min, plane, c, es);
         for (int i = threadIdx.x; i < SWD * GI_TH; i += blockDim.x) {
             int row = i / SWD, col = i - row * SWD;
             int gy = y0 + row;
             if (gy >= h) continue;
             int gx = clampi(x0 - m + col, 0, w - 1);
-            float v = Mc[(size_t)gy * pitch + gx] * t.k[0];
+            float v = Mc[((size_t)gy * pitch + gx) * es] * t.k[0];
             for (int k = 1; k <= m; k++)
-                v = v + (Mc[(size_t)min(gy + k, h - 1) * pitch + gx] + Mc[(size_t)max(gy - k, 0) * pitch + gx]) * t.k[k];
+                v = v + (Mc[((size_t)min(gy + k, h - 1) * pitch + gx) * es] + Mc[((size_t)max(gy - k, 0) * pitch + gx) * es]) * t.k[k];
             gi_smem[i] = v;
         }
         __syncthreads();
@@ -568,6 +589,52 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
 constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_RV = 16;
 constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
 
+// phase U of K4/K5: lane = x, coalesced.  Last iteration: write the flow tile; otherwise the next update-matrices.
+__device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *__restrict__ Fb, int tid, int x0, int y0, int b)
+{
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const size_t plane = a.d.plane;
+    if (a.last) {
+        float *f = a.flow + (size_t)b * 2 * plane;
+#pragma unroll 4
+        for (int i = tid; i < GK_TW * GK_TH; i += 256) {
+            const int row = i / GK_TW, col = i - row * GK_TW;
+            const int x = x0 + col, y = y0 + row;
+            if (x >= w || y >= h) continue;
+            const size_t o = (size_t)y * pitch + x;
+            f[o] = Fb[row * GK_FP + col];
+            f[o + plane] = Fb[(GK_TH + row) * GK_FP + col];
+        }
+        return;
+    }
+    const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
+    float *M = a.Mout + (size_t)b * 5 * plane;
+    // 12 pixels per thread, in 4 rounds of 3: all loads of a round are in flight together
+#pragma unroll 1
+    for (int rnd = 0; rnd < 4; rnd++) {
+        UpdLoad L[3];
+        float fx[3], fy[3];
+        int xs[3], ys[3];
+        bool ok[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int i = tid + (rnd * 3 + u) * 256;
+            const int row = i / GK_TW, col = i - row * GK_TW;
+            xs[u] = x0 + col; ys[u] = y0 + row;
+            ok[u] = xs[u] < w && ys[u] < h;
+            fx[u] = Fb[row * GK_FP + col]; fy[u] = Fb[(GK_TH + row) * GK_FP + col];
+            if (ok[u]) upd_load(R0, R1, plane, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            if (!ok[u]) continue;
+            float mm[5];
+            upd_compute(L[u], w, h, xs[u], ys[u], fx[u], fy[u], mm);
+            store_M(M, plane, (size_t)ys[u] * pitch + xs[u], mm);
+        }
+    }
+}
+
 template <int MR, bool FMA, bool INTERIOR>
 __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, float *__restrict__ Vb, const WinTaps &t, int tid, int x0,
                                               int y0, int w, int h, int pitch, size_t plane)
@@ -577,15 +644,17 @@ __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, flo
     const int ybase = y0 + g * GK_RV - MR;
 #pragma unroll 1
     for (int c = 0; c < 5; c++) {
-        const float *Mc = Min + c * plane + gx;
+        int es;
+        const float *Mc = M_channel(Min, plane, c, es) + (size_t)gx * es;
+        const size_t rs = (size_t)pitch * es;
         float in[GK_RV + 2 * MR];
         if (INTERIOR) {
-            const float *p = Mc + (size_t)ybase * pitch;
+            const float *p = Mc + (size_t)ybase * rs;
 #pragma unroll
-            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(p + (size_t)r * pitch);
+            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(p + (size_t)r * rs);
         } else {
 #pragma unroll
-            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(Mc + (size_t)clampi(ybase + r, 0, h - 1) * pitch);
+            for (int r = 0; r < GK_RV + 2 * MR; r++) in[r] = __ldg(Mc + (size_t)clampi(ybase + r, 0, h - 1) * rs);
         }
         float *dst = Vb + (c * GK_TH + g * GK_RV) * GK_VP + j;
 #pragma unroll
@@ -671,48 +740,267 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     }
     __syncthreads();
 
-    // ---- phase U: coalesced epilogue ----
-    if (a.last) {
-        float *f = a.flow + (size_t)b * 2 * plane;
-#pragma unroll 4
-        for (int i = tid; i < GK_TW * GK_TH; i += 256) {
-            const int row = i / GK_TW, col = i - row * GK_TW;
-            const int x = x0 + col, y = y0 + row;
-            if (x >= w || y >= h) continue;
-            const size_t o = (size_t)y * pitch + x;
-            f[o] = Fb[row * GK_FP + col];
-            f[o + plane] = Fb[(GK_TH + row) * GK_FP + col];
-        }
-        return;
+    gauss_epilogue(a, Fb, tid, x0, y0, b);
+}
+
+
+// Packed f32x2 arithmetic (sm_100+), written as PTX with explicit .rn so that neither NVVM nor ptxas may contract a
+// multiply and an add into an FFMA2: each half is one IEEE-754 operation, exactly like the scalar oracle code.
+// (The CUDA intrinsics __fmul2_rn + __fadd2_rn WERE contracted into FFMA2 by nvcc 12.9 even with -fmad=false.)
+__device__ __forceinline__ unsigned long long f2_pack(float2 v)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r)
+{
+    float2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ float2 tw_add2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ float2 tw_mul2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+// NOTE: ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2 even with --fmad false (the scalar
+// mul.rn/add.rn pair is respected).  The faithful accumulate "v + p" is therefore issued as fma(p, one, v) with
+// `one` a RUNTIME 1.0f (WinTaps.one): p * 1.0 is exact, so the result is round(p + v) -- one IEEE add -- and ptxas
+// cannot fold it because it does not know the value.
+__device__ __forceinline__ float2 tw_fma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4/K5 v2: the same tile / phase structure as gauss_iter_kernel, with the tap sums issued as PACKED f32x2
+// instructions (FADD2 / FMUL2 / FFMA2, sm_100+).  Each half of a packed op is an independent IEEE-754 op, so the
+// result stays bit-identical to the oracle's scalar add-mul-add order while the FP32 instruction count halves
+// (measured, tools/ubench2.cu: the faithful tap runs 1.41x faster packed than scalar).
+//   Packing: phase V pairs the CHANNELS (G11,G12) and (G22,h1) of one pixel column, and for h2 two adjacent
+//   columns; phase H reads them back as float2 (pitch 130 float2 = conflict-free LDS.128 with lane = row) and
+//   pairs h2 over adjacent pixels.  Shared: P01[32][130] float2, P23[32][130] float2, P4[32][132] float, flow tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int G2_P2 = 130, G2_P4 = 132, G2_RV = 8;
+constexpr size_t G2_SMEM = sizeof(float) * (2 * GK_TH * G2_P2 * 2 + GK_TH * G2_P4 + 2 * GK_TH * GK_FP);
+
+template <int MR, bool FMA, bool INTERIOR>
+__device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
+                                              int dstride, int ybase, int h, const WinTaps &t)
+{
+    constexpr int NIN = G2_RV + 2 * MR;
+    const float2 one2 = make_float2(t.one, t.one);
+    float2 in[NIN];
+    if (INTERIOR) {
+        src += (size_t)ybase * rstride;
+#pragma unroll
+        for (int r = 0; r < NIN; r++) in[r] = __ldg(src + (size_t)r * rstride);
+    } else {
+#pragma unroll
+        for (int r = 0; r < NIN; r++) in[r] = __ldg(src + (size_t)clampi(ybase + r, 0, h - 1) * rstride);
     }
-    const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
-    float *M = a.Mout + (size_t)b * 5 * plane;
-    // 12 pixels per thread, in 4 rounds of 3: all loads of a round are in flight together
+#pragma unroll
+    for (int o = 0; o < G2_RV; o++) {
+        float2 v = tw_mul2(in[o + MR], make_float2(t.k[0], t.k[0]));
+#pragma unroll
+        for (int i = 1; i <= MR; i++) {
+            const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
+            const float2 kk = make_float2(t.k[i], t.k[i]);
+            if (FMA) v = tw_fma2(sum, kk, v);
+            else v = tw_fma2(tw_mul2(sum, kk), one2, v); // = v + round(sum * k): see tw_fma2 note
+        }
+        dst[o * dstride] = v;
+    }
+}
+
+// 5 items per thread: (G11,G12) and (G22,h1) float2 planes at (column j, row groups g and g+2), then the h2 plane at
+// (column pair jj, row group g) -- every item is "38 8-byte loads, 8 packed outputs".  Columns are replicated by
+// clamping the address; the h2 column pair is clamped as a pair (x0 and w are even multiples of the tile / pitch
+// except at the right edge, where both columns clamp to w-1 via the scalar fallback).
+template <int MR, bool FMA, bool INTERIOR>
+__device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, float *__restrict__ sm, const WinTaps &t, int tid, int x0,
+                                               int y0, int w, int h, int pitch, size_t plane)
+{
+    float2 *P01 = reinterpret_cast<float2 *>(sm);
+    float2 *P23 = P01 + GK_TH * G2_P2;
+    float2 *P4 = P23 + GK_TH * G2_P2; // float2 view of the plain float plane (pitch 132 floats = 66 float2)
 #pragma unroll 1
-    for (int rnd = 0; rnd < 4; rnd++) {
-        UpdLoad L[3];
-        float fx[3], fy[3];
-        int xs[3], ys[3];
-        bool ok[3];
+    for (int it = 0; it < 4; it++) {
+        const int pair = it >> 1, j = tid & 127, g = (tid >> 7) + 2 * (it & 1);
+        const int gx = clampi(x0 - 16 + j, 0, w - 1);
+        const float2 *src = reinterpret_cast<const float2 *>(Min + (size_t)pair * 2 * plane) + gx;
+        float2 *dst = (pair ? P23 : P01) + g * G2_RV * G2_P2 + j;
+        gauss_v_item2<MR, FMA, INTERIOR>(src, pitch, dst, G2_P2, y0 + g * G2_RV - MR, h, t);
+    }
+    {
+        const int jj = tid & 63, g = tid >> 6;
+        const int xa = x0 - 16 + 2 * jj;
+        float2 *dst = P4 + g * G2_RV * (G2_P4 / 2) + jj;
+        const float *P = Min + 4 * plane;
+        if (xa >= 0 && xa + 1 <= w - 1) {
+            gauss_v_item2<MR, FMA, INTERIOR>(reinterpret_cast<const float2 *>(P + xa), pitch / 2, dst, G2_P4 / 2, y0 + g * G2_RV - MR, h, t);
+        } else { // edge column pair: clamp each column separately (scalar loads)
+            const int ca = clampi(xa, 0, w - 1), cb = clampi(xa + 1, 0, w - 1), ybase = y0 + g * G2_RV - MR;
+            constexpr int NIN = G2_RV + 2 * MR;
+            const float2 one2 = make_float2(t.one, t.one);
+            float2 in[NIN];
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const int i = tid + (rnd * 3 + u) * 256;
-            const int row = i / GK_TW, col = i - row * GK_TW;
-            xs[u] = x0 + col; ys[u] = y0 + row;
-            ok[u] = xs[u] < w && ys[u] < h;
-            fx[u] = Fb[row * GK_FP + col]; fy[u] = Fb[(GK_TH + row) * GK_FP + col];
-            if (ok[u]) upd_load(R0, R1, plane, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
-        }
+            for (int r = 0; r < NIN; r++) {
+                const size_t o = (size_t)clampi(ybase + r, 0, h - 1) * pitch;
+                in[r] = make_float2(__ldg(P + o + ca), __ldg(P + o + cb));
+            }
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
-            if (!ok[u]) continue;
-            float mm[5];
-            upd_compute(L[u], w, h, xs[u], ys[u], fx[u], fy[u], mm);
-            const size_t o = (size_t)ys[u] * pitch + xs[u];
+            for (int o = 0; o < G2_RV; o++) {
+                float2 v = tw_mul2(in[o + MR], make_float2(t.k[0], t.k[0]));
 #pragma unroll
-            for (int c = 0; c < 5; c++) M[o + c * plane] = mm[c];
+                for (int i = 1; i <= MR; i++) {
+                    const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
+                    const float2 kk = make_float2(t.k[i], t.k[i]);
+                    if (FMA) v = tw_fma2(sum, kk, v);
+                    else v = tw_fma2(tw_mul2(sum, kk), one2, v);
+                }
+                dst[o * (G2_P4 / 2)] = v;
+            }
         }
     }
+}
+
+template <int MR, bool FMA>
+__global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps t)
+{
+    extern __shared__ __align__(16) float gk_smem[];
+    float *Fb = gk_smem + 2 * GK_TH * G2_P2 * 2 + GK_TH * G2_P4;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = blockIdx.x * GK_TW, y0 = blockIdx.y * GK_TH, b = blockIdx.z;
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const size_t plane = a.d.plane;
+    const float *Min = a.Min + (size_t)b * 5 * plane;
+
+    // Every V item starts with a burst of loads whose latency is exposed (registers leave no room for double
+    // buffering): pull the tile's M rows (all 5 planes, with halo) from DRAM into L2 up front, so that items 1..4 see
+    // L2 latency; likewise the epilogue's R0 / R1 lines.
+    {
+        constexpr int NR = GK_TH + 2 * MR, NL = 20; // rows x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
+        const int xl = max(x0 - 16, 0);
+        for (int i = tid; i < NR * NL; i += 256) {
+            const int row = i / NL, seg = i - row * NL;
+            const int y = clampi(y0 - MR + row, 0, h - 1);
+            const float *p;
+            if (seg < 16) p = Min + (size_t)(seg >> 3) * 2 * plane + ((size_t)y * pitch + min(xl + (seg & 7) * 16, w - 1)) * 2;
+            else p = Min + 4 * plane + (size_t)y * pitch + min(xl + (seg - 16) * 32, w - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
+    if (!a.last) {
+        const float *Rb = a.R + (size_t)b * 10 * plane;
+        for (int i = tid; i < 10 * GK_TH * 3; i += 256) {
+            const int pl = i / (GK_TH * 3), rem = i - pl * (GK_TH * 3), row = rem / 3, seg = rem - row * 3;
+            const int y = min(y0 + row, h - 1), x = min(x0 + seg * 32, w - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + pl * plane + (size_t)y * pitch + x));
+        }
+    }
+
+    // ---- phase V (packed) ----
+    if ((y0 - MR >= 0) && (y0 + GK_TH + MR - 1 <= h - 1))
+        gauss_v_phase2<MR, FMA, true>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+    else
+        gauss_v_phase2<MR, FMA, false>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+    __syncthreads();
+
+    // ---- phase H (packed) + solve ----
+    {
+        const float2 *P01 = reinterpret_cast<const float2 *>(gk_smem);
+        const float2 *P23 = P01 + GK_TH * G2_P2;
+        const float *P4 = gk_smem + 2 * GK_TH * G2_P2 * 2;
+        const int seg = tid >> 5;
+        constexpr int LO = (16 - MR) & ~3;
+        constexpr int NV = ((3 + 16 + MR) | 3) + 1 - LO;
+        const float2 one2 = make_float2(t.one, t.one);
+#pragma unroll 1
+        for (int grp = 0; grp < 3; grp++) {
+            const int cbase = seg * 12 + grp * 4;
+            float2 r01[4], r23[4];
+            float r4[4];
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                const float4 *src = reinterpret_cast<const float4 *>((pr ? P23 : P01) + lane * G2_P2 + cbase + LO);
+                float2 v[NV];
+#pragma unroll
+                for (int q = 0; q < NV / 2; q++) {
+                    const float4 u = src[q];
+                    v[2 * q] = make_float2(u.x, u.y); v[2 * q + 1] = make_float2(u.z, u.w);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int ctr = p + 16 - LO;
+                    float2 sacc = tw_mul2(v[ctr], make_float2(t.k[0], t.k[0]));
+#pragma unroll
+                    for (int i = 1; i <= MR; i++) {
+                        const float2 sum = tw_add2(v[ctr - i], v[ctr + i]);
+                        const float2 kk = make_float2(t.k[i], t.k[i]);
+                        if (FMA) sacc = tw_fma2(kk, sum, sacc);
+                        else sacc = tw_fma2(tw_mul2(kk, sum), one2, sacc);
+                    }
+                    if (pr) r23[p] = sacc; else r01[p] = sacc;
+                }
+            }
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(P4 + lane * G2_P4 + cbase + LO);
+                float v[NV];
+#pragma unroll
+                for (int q = 0; q < NV / 4; q++) {
+                    const float4 u = src[q];
+                    v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p += 2) { // pixels (p, p+1) packed
+                    const int ctr = p + 16 - LO;
+                    float2 sacc = tw_mul2(make_float2(v[ctr], v[ctr + 1]), make_float2(t.k[0], t.k[0]));
+#pragma unroll
+                    for (int i = 1; i <= MR; i++) {
+                        const float2 sum = tw_add2(make_float2(v[ctr - i], v[ctr + 1 - i]), make_float2(v[ctr + i], v[ctr + 1 + i]));
+                        const float2 kk = make_float2(t.k[i], t.k[i]);
+                        if (FMA) sacc = tw_fma2(kk, sum, sacc);
+                        else sacc = tw_fma2(tw_mul2(kk, sum), one2, sacc);
+                    }
+                    r4[p] = sacc.x; r4[p + 1] = sacc.y;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float fx, fy;
+                solve2x2(r01[p].x, r01[p].y, r23[p].x, r23[p].y, r4[p], fx, fy);
+                Fb[lane * GK_FP + cbase + p] = fx;
+                Fb[(GK_TH + lane) * GK_FP + cbase + p] = fy;
+            }
+        }
+    }
+    __syncthreads();
+    gauss_epilogue(a, Fb, tid, x0, y0, b);
+}
+
+template <int MR, bool FMA>
+static cudaError_t launch_gauss_fast2(cudaStream_t s, const IterArgs &a, const WinTaps &t)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
+    gauss_iter2_kernel<MR, FMA><<<grid, 256, G2_SMEM, s>>>(a, t);
+    return cudaGetLastError();
 }
 
 template <int MR, bool FMA>
@@ -731,6 +1019,10 @@ static cudaError_t launch_gauss_fast(cudaStream_t s, const IterArgs &a, const Wi
 
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
+    if (!a.scalar) {
+        if (t.m == 15) return a.fma ? launch_gauss_fast2<15, true>(s, a, t) : launch_gauss_fast2<15, false>(s, a, t);
+        if (t.m == 7) return a.fma ? launch_gauss_fast2<7, true>(s, a, t) : launch_gauss_fast2<7, false>(s, a, t);
+    }
     if (t.m == 15) return a.fma ? launch_gauss_fast<15, true>(s, a, t) : launch_gauss_fast<15, false>(s, a, t);
     if (t.m == 7) return a.fma ? launch_gauss_fast<7, true>(s, a, t) : launch_gauss_fast<7, false>(s, a, t);
     dim3 grid((a.d.w + GI_TW - 1) / GI_TW, (a.d.h + GI_TH - 1) / GI_TH, a.batch);
@@ -754,9 +1046,10 @@ __global__ void __launch_bounds__(128) box_vsum_kernel(const float *__restrict__
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= d.w) return;
-    const float *M = Min + (size_t)blockIdx.y * d.plane + x;
+    int es;
+    const float *M = M_channel(Min + (size_t)(blockIdx.y / 5) * 5 * d.plane, d.plane, blockIdx.y % 5, es) + (size_t)x * es;
     double *v = VT + (size_t)blockIdx.y * planeT + (size_t)x * pitchT;
-    const int h = d.h, pitch = d.pitch;
+    const int h = d.h, pitch = d.pitch * es;
     double vs = (double)(M[0] * (float)(m + 2));
     for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * pitch];
 #pragma unroll 4

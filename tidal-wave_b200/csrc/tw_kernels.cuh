@@ -23,6 +23,7 @@ struct PolyTables {
 
 struct WinTaps {
     float k[kMaxWinRadius + 1];
+    float one; // 1.0f, deliberately a runtime value (see tw_fma2 in tw_kernels.cu)
     int m;
 };
 
@@ -76,6 +77,7 @@ struct IterArgs {
     LevelDims d;
     int batch;
     int last;
+    int scalar; // 1: scalar FP32 tap sums (v1 kernel) instead of packed f32x2
     int fma; // validated relaxation: fmaf in the Gaussian tap sums (never set for the box window)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);

@@ -2,8 +2,7 @@
 
 The path shards by independent units (image pairs): there is NO data-path collective.  The only
 cross-rank traffic is (i) the barrier around the timed region, (ii) a MAX over ranks of the timed duration and
-(iii) a SUM of the Report counters (/root/reference/src/message_queue.h:44-48) at the end.  Backend: nccl on GPUs,
-gloo on CPU (tests).
+(iii) a SUM of the Report counters (/root/reference/src/message_queue.h:44-48) at the end.  Backend: gloo (CPU tensors).
 """
 from __future__ import annotations
 
@@ -21,15 +20,15 @@ class Dist:
             import torch
             import torch.distributed as dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # The path has no data-path collective (independent pairs), so the process group only carries a barrier and
+            # three scalars: gloo on CPU tensors does that without touching the GPUs (and without NCCL's stdout banner,
+            # which would break the one-JSON-line contract of bench.py).  backend="nccl" remains selectable.
             if backend is None:
-                backend = "nccl" if torch.cuda.is_available() else "gloo"
+                backend = "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-                try:
-                    dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
-                    self.device = "cuda"
-                except Exception:
-                    dist.init_process_group("gloo")
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                self.device = "cuda"
             else:
                 dist.init_process_group(backend)
             self.pg = dist
