@@ -29,6 +29,8 @@ struct Scale {
     float *img_xf = nullptr, *img_yf = nullptr, *up_xf = nullptr, *up_yf = nullptr;
     float *taps = nullptr;
     int tile_w = 32, tile_h = 8, smem_w = 0, smem_h = 0, identity = 0;
+    int int_scale = 0;            // S if the level is an exact integer down-scale with 0.5/0.5 taps (fast path), else 0
+    std::vector<float> host_taps;
     // buffers (alias the shared work buffers unless keep_levels)
     float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr, *flow = nullptr;
 };
@@ -56,7 +58,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
-    int opt_gauss_fma = 0, opt_gauss_scalar = 0;
+    int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -295,12 +297,13 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
             int sw = 0, sh = 0;
             for (int d0 = 0; d0 < s.d.w; d0 += tw_) {
                 int d1 = std::min(d0 + tw_, s.d.w) - 1;
-                sw = std::max(sw, std::min(xi[d1] + 1, W - 1) + c - (xi[d0] - c) + 1);
+                sw = std::max(sw, std::min(xi[d1] + 1, W - 1) + c - ((xi[d0] - c) & ~3) + 1);
             }
             for (int e0 = 0; e0 < s.d.h; e0 += th_) {
                 int e1 = std::min(e0 + th_, s.d.h) - 1;
                 sh = std::max(sh, std::min(yi[e1] + 1, H - 1) + c - (yi[e0] - c) + 1);
             }
+            sw = (sw + 3 + 4) & ~3; // the staging loop writes whole 4-column words
             size_t bytes = level_image_smem_bytes(sw, sh, tw_, s.ksize, s.identity);
             if (bytes <= 64 * 1024 || (tw_ == 1 && th_ == 1)) {
                 if (bytes > 200 * 1024) { ctx->err = "pre-blur kernel too large for shared memory"; return false; }
@@ -313,7 +316,17 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         if (!dev_upload(ctx, &s.img_xi, xi) || !dev_upload(ctx, &s.img_xf, xf) || !dev_upload(ctx, &s.img_yi, yi) ||
             !dev_upload(ctx, &s.img_yf, yf))
             return false;
-        if (!dev_upload(ctx, &s.taps, gauss_taps(s.ksize, s.sigma))) return false;
+        s.host_taps = gauss_taps(s.ksize, s.sigma);
+        if (!dev_upload(ctx, &s.taps, s.host_taps)) return false;
+        // exact integer down-scale?  (tables xi/xf/yi/yf still hold the image-resize coefficients here)
+        s.int_scale = 0;
+        if (!s.identity && s.d.w > 0 && W % s.d.w == 0 && H % s.d.h == 0 && W / s.d.w == H / s.d.h) {
+            const int S = W / s.d.w;
+            bool ok = (S % 2 == 0);
+            for (int d = 0; ok && d < s.d.w; d++) ok = (xi[d] == S * d + S / 2 - 1) && (xf[d] == 0.5f);
+            for (int e = 0; ok && e < s.d.h; e++) ok = (yi[e] == S * e + S / 2 - 1) && (yf[e] == 0.5f);
+            if (ok) s.int_scale = S;
+        }
         if (si > 0) {
             const Scale &cs = pl.scales[si - 1];
             resize_coeffs(cs.d.w, s.d.w, xi, xf);
@@ -406,6 +419,12 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
     const int W = pl.W, H = pl.H;
     const double P0 = (double)W * H;
     const size_t ns = pl.scales.size();
+    // sampling is fused into the last Gaussian iteration of the finest scale when that kernel runs (radius 15 / 7)
+    const bool fused_count = span > 0 && (p.flags & 256) && p.pyrIterations > 0 && (pl.win.m == 15 || pl.win.m == 7);
+    if (fused_count) {
+        cudaError_t e = cudaMemsetAsync(ctx->d_counts, 0, sizeof(int) * n, ctx->stream);
+        if (e != cudaSuccess) { set_err(ctx, "memset counts", e); return false; }
+    }
     for (size_t si = 0; si < ns; si++) {
         Scale &s = pl.scales[si];
         const double Pl = (double)s.d.w * s.d.h;
@@ -416,7 +435,12 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         la.identity = s.identity;
         la.small = (s.ksize / 2 + 2 >= std::min(W, H));
         // I planes of a batch are laid out [B][2]: the u8 source is [B][2] too, so image index = blockIdx.z.
-        LAUNCH(F_LEVEL, n * (2 * P0 + 8 * Pl), launch_level_image(ctx->stream, la));
+        {
+            LaunchScope ls_(ctx, F_LEVEL, n * (2 * P0 + 8 * Pl));
+            cudaError_t e_ = ctx->opt_level_generic ? cudaErrorNotSupported : launch_level_image_fast(ctx->stream, la, s.host_taps.data(), s.int_scale);
+            if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
+            if (e_ != cudaSuccess) { set_err(ctx, "launch_level_image", e_); return false; }
+        }
         LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly));
 
         FirstUpdateArgs fa{};
@@ -436,6 +460,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             IterArgs ia{};
             ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
             ia.last = (it == p.pyrIterations - 1);
+            if (fused_count && ia.last && si + 1 == ns) { ia.span = span; ia.thr2 = threshold * threshold; ia.counts = ctx->d_counts; }
             ia.fma = ctx->opt_gauss_fma;
             ia.scalar = ctx->opt_gauss_scalar;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
@@ -460,7 +485,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         if (!ensure_results(ctx, nsx * nsy)) return false;
         SampleArgs sa{};
         sa.flow = f.flow; sa.d = f.d; sa.batch = n; sa.span = span; sa.thr2 = threshold * threshold;
-        sa.counts = ctx->d_counts; sa.vectors = ctx->d_vectors; sa.cap = ctx->dev_cap;
+        sa.counts = ctx->d_counts; sa.vectors = ctx->d_vectors; sa.cap = ctx->dev_cap; sa.counted = fused_count ? 1 : 0;
         LAUNCH(F_SAMPLE, 0.0, launch_sample(ctx->stream, sa));
     }
     return true;
@@ -795,6 +820,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!ctx || !name) return TW_BAD_PARAMETER;
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;
 }

@@ -45,10 +45,12 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
     const int tw_ = d1 - d0 + 1, th_ = e1 - e0 + 1;
     const int W = a.W, H = a.H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // source tile (unclamped extents; border pixels are staged through REFLECT_101 so the tap loops index directly)
-    const int xs_lo = a.xi[d0] - c, ys_lo = a.yi[e0] - c;
+    // source tile (unclamped extents; border pixels are staged through REFLECT_101 so the tap loops index directly).
+    // The tile origin is aligned down to 4 source columns so that interior words are staged with one 4-byte load,
+    // two instructions per pixel for the exact u8 -> float conversion (PRMT + FADD) and one 16-byte shared store.
+    const int xs_lo = (a.xi[d0] - c) & ~3, ys_lo = a.yi[e0] - c;
     const int SW = min(a.xi[d1] + 1, W - 1) + c - xs_lo + 1, SH = min(a.yi[e1] + 1, H - 1) + c - ys_lo + 1;
-    const int SWp = a.smem_w | 1; // odd pitch
+    const int SWp = a.smem_w; // multiple of 4
     const int NC = IDENT ? a.tile_w : a.tile_w * 2;
     float *tile = li_smem;                        // [smem_h][SWp]
     float *rp = tile + (size_t)a.smem_h * SWp;    // [smem_h][NC]
@@ -62,17 +64,35 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
             for (int q = lane; q < SW; q += 32) tile[r * SWp + q] = u8_to_float(srow[reflect101(xs_lo + q, W)]);
         }
     } else {
-        // independent byte loads (ld.global.nc), 2 rows x 4 columns in flight per thread: this phase is latency-bound
+        const int nwords = (SW + 3) >> 2;
         for (int r = warp; r < SH; r += 16) {
             const int r2 = min(r + 8, SH - 1);
             const uint8_t *srow0 = src + (size_t)reflect1(ys_lo + r, H) * a.spitch;
             const uint8_t *srow1 = src + (size_t)reflect1(ys_lo + r2, H) * a.spitch;
-#pragma unroll 4
-            for (int q = lane; q < SW; q += 32) {
-                const int gx = reflect1(xs_lo + q, W);
-                const unsigned b0 = __ldg(srow0 + gx), b1 = __ldg(srow1 + gx);
-                tile[r * SWp + q] = u8_to_float(b0);
-                tile[r2 * SWp + q] = u8_to_float(b1);
+#pragma unroll 2
+            for (int q4 = lane; q4 < nwords; q4 += 32) {
+                const int gx = xs_lo + 4 * q4;
+                float4 f0, f1;
+                if (gx >= 0 && gx + 3 < W) {
+                    const unsigned w0 = __ldg(reinterpret_cast<const unsigned *>(srow0 + gx));
+                    const unsigned w1 = __ldg(reinterpret_cast<const unsigned *>(srow1 + gx));
+                    f0.x = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7650)) - 8388608.0f;
+                    f0.y = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7651)) - 8388608.0f;
+                    f0.z = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7652)) - 8388608.0f;
+                    f0.w = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7653)) - 8388608.0f;
+                    f1.x = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7650)) - 8388608.0f;
+                    f1.y = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7651)) - 8388608.0f;
+                    f1.z = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7652)) - 8388608.0f;
+                    f1.w = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7653)) - 8388608.0f;
+                } else {
+                    const int g0 = reflect1(gx, W), g1 = reflect1(gx + 1, W), g2 = reflect1(gx + 2, W), g3 = reflect1(gx + 3, W);
+                    f0 = make_float4(u8_to_float(__ldg(srow0 + g0)), u8_to_float(__ldg(srow0 + g1)), u8_to_float(__ldg(srow0 + g2)),
+                                     u8_to_float(__ldg(srow0 + g3)));
+                    f1 = make_float4(u8_to_float(__ldg(srow1 + g0)), u8_to_float(__ldg(srow1 + g1)), u8_to_float(__ldg(srow1 + g2)),
+                                     u8_to_float(__ldg(srow1 + g3)));
+                }
+                *reinterpret_cast<float4 *>(tile + r * SWp + 4 * q4) = f0;
+                *reinterpret_cast<float4 *>(tile + r2 * SWp + 4 * q4) = f1;
             }
         }
     }
@@ -82,7 +102,7 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
     const int ncol = IDENT ? tw_ : tw_ * 2;
     for (int slot = lane; slot < ncol; slot += 32) {
         int xl; // local column of tap 0
-        if (IDENT) xl = slot;
+        if (IDENT) xl = d0 + slot - c - xs_lo;
         else xl = min(a.xi[d0 + (slot >> 1)] + (slot & 1), W - 1) - c - xs_lo;
         if (K == 3) {
             const float k0 = ktab[0], k1 = ktab[1];
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
 
 size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity)
 {
-    return sizeof(float) * ((size_t)smem_h * (smem_w | 1) + (size_t)smem_h * (identity ? tile_w : tile_w * 2) + ksize);
+    return sizeof(float) * ((size_t)smem_h * smem_w + (size_t)smem_h * (identity ? tile_w : tile_w * 2) + ksize);
 }
 
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a)
@@ -159,6 +179,209 @@ cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a)
     if (a.identity) level_image_kernel<true><<<grid, 256, smem, s>>>(a);
     else level_image_kernel<false><<<grid, 256, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast paths.  The generic kernel above handles any pyrScale; these two cover what the reference's default
+// pyrScale = 0.5 produces whenever the frame size is divisible by the scale: (a) the full-resolution level
+// (3-tap blur, no resize) and (b) exact integer down-scales S = 2, 4, 8, 16 where the bilinear resize reads
+// source columns/rows S*d + S/2 - 1 and S*d + S/2 with weight 0.5 each (checked on the host against the A.2b
+// tables).  Compile-time tile geometry: taps from the constant bank, no index arithmetic in the tap loops,
+// lane = source row with a 4*odd shared pitch so that the row pass reads its K+1 inputs as conflict-free LDS.128.
+// ------------------------------------------------------------------------------------------------
+struct LevelFastArgs {
+    const uint8_t *src; // [nimg][H][spitch]
+    int W, H, spitch;
+    float *dst;         // [nimg][h][pitch]
+    LevelDims d;
+    float k[40];        // ksize taps
+};
+
+template <int SH, int SWP>
+__device__ __forceinline__ void stage_tile_u8(const uint8_t *__restrict__ src, int spitch, int W, int H, int xs_lo, int ys_lo,
+                                              float *__restrict__ tile, int warp, int lane)
+{
+    constexpr int NW = SWP / 4;
+#pragma unroll 4
+    for (int r = warp; r < SH; r += 8) {
+        const uint8_t *srow = src + (size_t)reflect1(ys_lo + r, H) * spitch;
+#pragma unroll
+        for (int q4 = lane; q4 < NW; q4 += 32) {
+            const int gx = xs_lo + 4 * q4;
+            float4 f;
+            if (gx >= 0 && gx + 3 < W) {
+                const unsigned w0 = __ldg(reinterpret_cast<const unsigned *>(srow + gx));
+                f.x = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7650)) - 8388608.0f;
+                f.y = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7651)) - 8388608.0f;
+                f.z = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7652)) - 8388608.0f;
+                f.w = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7653)) - 8388608.0f;
+            } else {
+                f = make_float4(u8_to_float(__ldg(srow + reflect1(gx, W))), u8_to_float(__ldg(srow + reflect1(gx + 1, W))),
+                                u8_to_float(__ldg(srow + reflect1(gx + 2, W))), u8_to_float(__ldg(srow + reflect1(gx + 3, W))));
+            }
+            *reinterpret_cast<float4 *>(tile + r * SWP + 4 * q4) = f;
+        }
+    }
+}
+
+// (a) full resolution: out = colpass3(rowpass3(u8)), tile 128 x 32, thread = column x 16 rows with a rolling window.
+constexpr int LI_TW = 128, LI_TH = 32, LI_SH = LI_TH + 2, LI_SWP = LI_TW + 8;
+
+__global__ void __launch_bounds__(256) level_ident_kernel(LevelFastArgs a)
+{
+    __shared__ __align__(16) float tile[LI_SH * LI_SWP];
+    const int x0 = blockIdx.x * LI_TW, y0 = blockIdx.y * LI_TH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t *src = a.src + (size_t)blockIdx.z * a.H * a.spitch;
+    stage_tile_u8<LI_SH, LI_SWP>(src, a.spitch, a.W, a.H, x0 - 4, y0 - 1, tile, warp, lane);
+    __syncthreads();
+    const int col = threadIdx.x & (LI_TW - 1), g = threadIdx.x >> 7;
+    const int x = x0 + col;
+    if (x >= a.d.w) return;
+    const float k0 = a.k[0], k1 = a.k[1];
+    const float *p = tile + (g * 16) * LI_SWP + col + 3; // left neighbour of column x in tile row g*16 (source row y0-1+g*16)
+    float *dst = a.dst + (size_t)blockIdx.z * a.d.plane + x;
+    float h0 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+    p += LI_SWP;
+    float h1 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        p += LI_SWP;
+        const float h2 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+        const int y = y0 + g * 16 + i;
+        if (y < a.d.h) dst[(size_t)y * a.d.pitch] = fmaf(h0 + h2, k0, h1 * k1);
+        h0 = h1; h1 = h2;
+    }
+}
+
+// (b) exact integer down-scale S with a K-tap pre-blur.
+template <int S, int K, int TWO, int THO>
+struct PyrGeom {
+    static constexpr int C = K / 2;
+    static constexpr int OFF = ((S / 2 - 1 - C) % 4 + 4) % 4;      // tile column of tap 0 of output column 0
+    static constexpr int SH = S * THO - S + 2 * C + 2;
+    static constexpr int SWRAW = S * TWO - S + 2 * C + 2 + OFF;
+    static constexpr int SW4 = (SWRAW + 3) / 4;
+    static constexpr int SWP = 4 * (SW4 | 1);                       // 4 * odd: conflict-free LDS.128 with lane = row
+    static constexpr int RPP = TWO + 1;                             // float2 pitch of the row-pass buffer
+    static constexpr int CPI = S >= 4 ? 1 : 4 / S;                  // output columns per row-pass item (keeps LDS.128 aligned)
+    static constexpr int NLD = (OFF + K + 1 + S * (CPI - 1) + 3) / 4; // float4 loads per row-pass item
+    static constexpr size_t SMEM = sizeof(float) * ((size_t)SH * SWP + (size_t)SH * RPP * 2);
+};
+
+template <int S, int K, int TWO, int THO>
+__global__ void __launch_bounds__(256) level_pyr_kernel(LevelFastArgs a)
+{
+    using G = PyrGeom<S, K, TWO, THO>;
+    constexpr int C = G::C;
+    extern __shared__ __align__(16) float lp_smem[];
+    float *tile = lp_smem;                                             // [SH][SWP]
+    float2 *rp = reinterpret_cast<float2 *>(lp_smem + G::SH * G::SWP);  // [SH][RPP] (slot 0, slot 1)
+    const int d0 = blockIdx.x * TWO, e0 = blockIdx.y * THO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t *src = a.src + (size_t)blockIdx.z * a.H * a.spitch;
+    const int xs_lo = S * d0 + S / 2 - 1 - C - G::OFF, ys_lo = S * e0 + S / 2 - 1 - C;
+    stage_tile_u8<G::SH, G::SWP>(src, a.spitch, a.W, a.H, xs_lo, ys_lo, tile, warp, lane);
+    __syncthreads();
+
+    // row pass: lane = tile row, warps stride over output columns; two adjacent source columns per item
+    for (int rb = 0; rb < G::SH; rb += 32) {
+        const int r = rb + lane;
+        if (r < G::SH) {
+            for (int dp = warp; dp < TWO / G::CPI; dp += 8) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(tile + r * G::SWP + S * G::CPI * dp);
+                float v[G::NLD * 4];
+#pragma unroll
+                for (int q = 0; q < G::NLD; q++) {
+                    const float4 u = p4[q];
+                    v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+                }
+#pragma unroll
+                for (int u = 0; u < G::CPI; u++) {
+                    constexpr int O = G::OFF;
+                    const int b = O + S * u;
+                    float o0, o1;
+                    if (K == 3) {
+                        o0 = fmaf(v[b + 1], a.k[1], (v[b] + v[b + 2]) * a.k[0]);
+                        o1 = fmaf(v[b + 2], a.k[1], (v[b + 1] + v[b + 3]) * a.k[0]);
+                    } else {
+                        o0 = v[b] * a.k[0];
+                        o1 = v[b + 1] * a.k[0];
+#pragma unroll
+                        for (int j = 1; j < K; j++) {
+                            o0 = fmaf(v[b + j], a.k[j], o0);
+                            o1 = fmaf(v[b + 1 + j], a.k[j], o1);
+                        }
+                    }
+                    rp[r * G::RPP + G::CPI * dp + u] = make_float2(o0, o1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // column pass at the two source rows each output row reads, then the 0.5 / 0.5 bilinear blend
+    float *dst = a.dst + (size_t)blockIdx.z * a.d.plane;
+    for (int i = threadIdx.x; i < TWO * THO; i += 256) {
+        const int el = i / TWO, dl = i - el * TWO;
+        const int d = d0 + dl, e = e0 + el;
+        if (d >= a.d.w || e >= a.d.h) continue;
+        const float2 *q = rp + (S * el + C) * G::RPP + dl; // source row y0 of this output row
+        float2 ra, rb2;
+        if (K == 3) {
+            const float2 u = q[-G::RPP], c0 = q[0], c1 = q[G::RPP], dn = q[2 * G::RPP];
+            ra = make_float2(fmaf(u.x + c1.x, a.k[0], c0.x * a.k[1]), fmaf(u.y + c1.y, a.k[0], c0.y * a.k[1]));
+            rb2 = make_float2(fmaf(c0.x + dn.x, a.k[0], c1.x * a.k[1]), fmaf(c0.y + dn.y, a.k[0], c1.y * a.k[1]));
+        } else {
+            const float2 c0 = q[0], c1 = q[G::RPP];
+            ra = make_float2(c0.x * a.k[C], c0.y * a.k[C]);
+            rb2 = make_float2(c1.x * a.k[C], c1.y * a.k[C]);
+#pragma unroll
+            for (int j = 1; j <= C; j++) {
+                const float2 am = q[-j * G::RPP], ap = q[j * G::RPP], bm = q[(1 - j) * G::RPP], bp = q[(1 + j) * G::RPP];
+                ra.x = fmaf(am.x + ap.x, a.k[C + j], ra.x); ra.y = fmaf(am.y + ap.y, a.k[C + j], ra.y);
+                rb2.x = fmaf(bm.x + bp.x, a.k[C + j], rb2.x); rb2.y = fmaf(bm.y + bp.y, a.k[C + j], rb2.y);
+            }
+        }
+        const float fx = 0.5f, gx = 1.f - fx, fy = 0.5f, gy = 1.f - fy;
+        const float r0 = ra.x * gx + ra.y * fx;
+        const float r1 = rb2.x * gx + rb2.y * fx;
+        dst[(size_t)e * a.d.pitch + d] = r0 * gy + r1 * fy;
+    }
+}
+
+template <int S, int K, int TWO, int THO>
+static cudaError_t launch_pyr(cudaStream_t s, const LevelFastArgs &fa, int nimg)
+{
+    using G = PyrGeom<S, K, TWO, THO>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(level_pyr_kernel<S, K, TWO, THO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((fa.d.w + TWO - 1) / TWO, (fa.d.h + THO - 1) / THO, nimg);
+    level_pyr_kernel<S, K, TWO, THO><<<grid, 256, G::SMEM, s>>>(fa);
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when no fast path applies (the caller then uses the generic kernel).
+cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, const float *host_taps, int int_scale)
+{
+    if (a.small || a.ksize > 40) return cudaErrorNotSupported;
+    LevelFastArgs fa{};
+    fa.src = a.src; fa.W = a.W; fa.H = a.H; fa.spitch = a.spitch; fa.dst = a.dst; fa.d = a.d;
+    for (int i = 0; i < a.ksize; i++) fa.k[i] = host_taps[i];
+    if (a.identity && a.ksize == 3) {
+        dim3 grid((a.d.w + LI_TW - 1) / LI_TW, (a.d.h + LI_TH - 1) / LI_TH, a.nimg);
+        level_ident_kernel<<<grid, 256, 0, s>>>(fa);
+        return cudaGetLastError();
+    }
+    if (int_scale == 2 && a.ksize == 3) return launch_pyr<2, 3, 64, 15>(s, fa, a.nimg);
+    if (int_scale == 4 && a.ksize == 9) return launch_pyr<4, 9, 32, 16>(s, fa, a.nimg);
+    if (int_scale == 8 && a.ksize == 19) return launch_pyr<8, 19, 16, 10>(s, fa, a.nimg);
+    if (int_scale == 16 && a.ksize == 39) return launch_pyr<16, 39, 8, 4>(s, fa, a.nimg);
+    return cudaErrorNotSupported;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -604,6 +827,23 @@ __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *_
             const size_t o = (size_t)y * pitch + x;
             f[o] = Fb[row * GK_FP + col];
             f[o + plane] = Fb[(GK_TH + row) * GK_FP + col];
+        }
+        if (a.span > 0) {
+            // sample points of this tile: multiples of span in [x0, x0+96) x [y0, y0+32); one per thread
+            const int sx0 = (x0 + a.span - 1) / a.span, sy0 = (y0 + a.span - 1) / a.span;
+            const int nsx = max(0, (min(x0 + GK_TW, w) - 1) / a.span - sx0 + 1), nsy = max(0, (min(y0 + GK_TH, h) - 1) / a.span - sy0 + 1);
+            int hit = 0;
+            for (int i = tid; i < nsx * nsy; i += 256) { // block-uniform trip count (<= 1 for span >= 4)
+                const int j = i / nsx, col = (sx0 + i - j * nsx) * a.span - x0, row = (sy0 + j) * a.span - y0;
+                const float dx = Fb[row * GK_FP + col], dy = Fb[(GK_TH + row) * GK_FP + col];
+                const float len = (dx * dx) + (dy * dy);
+                hit += ((double)len > a.thr2) ? 1 : 0;
+            }
+            if (nsx * nsy > 0) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) hit += __shfl_xor_sync(0xffffffffu, hit, off);
+                if ((tid & 31) == 0 && hit > 0) atomicAdd(a.counts + b, hit);
+            }
         }
         return;
     }
@@ -1137,6 +1377,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleArgs a)
     __shared__ int warp_sums[32];
     __shared__ int total;
     const int b = blockIdx.x;
+    if (a.counted && a.counts[b] == 0) return; // OK pair: nothing to compact (block-uniform)
     const float *fxp = a.flow + (size_t)b * 2 * a.d.plane, *fyp = fxp + a.d.plane;
     const int nsx = (a.d.w + a.span - 1) / a.span, nsy = (a.d.h + a.span - 1) / a.span, ns = nsx * nsy;
     const int per = (ns + blockDim.x - 1) / blockDim.x;

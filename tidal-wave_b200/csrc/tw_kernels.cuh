@@ -48,6 +48,9 @@ struct LevelImageArgs {
     int small;          // ksize/2 >= min(W, H): multi-bounce reflect path
 };
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a);
+// Fast paths (full-resolution level; exact integer down-scales 2/4/8/16).  int_scale = S if W == w*S, H == h*S and the
+// resize tables are exactly (S*d + S/2 - 1, 0.5), else 0.  Returns cudaErrorNotSupported if none applies.
+cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, const float *host_taps, int int_scale);
 size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity);
 
 // K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
@@ -77,6 +80,12 @@ struct IterArgs {
     LevelDims d;
     int batch;
     int last;
+    // span sampling fused into the last iteration of the finest scale (reference src/consumer.cpp:60-77): the
+    // threshold test runs on the flow tile while it is still in shared memory; per-pair counts are reduced with
+    // warp shuffles and one atomicAdd per warp.  span == 0: off.
+    int span;
+    double thr2;
+    int *counts; // [B], zeroed by the host before the launch
     int scalar; // 1: scalar FP32 tap sums (v1 kernel) instead of packed f32x2
     int fma; // validated relaxation: fmaf in the Gaussian tap sums (never set for the box window)
 };
@@ -95,6 +104,7 @@ struct SampleArgs {
     int span;
     double thr2; // threshold * threshold in double
     int *counts;       // [B]
+    int counted;       // counts[] already hold the totals (fused into K5): pairs with 0 vectors exit at once
     void *vectors;     // [B][cap] tw_vector {int x, int y, double dx, double dy}
     int cap;
 };
