@@ -99,6 +99,37 @@ def test_per_stage_parity(tw, oracle, golden, opt):
     of.close()
 
 
+@pytest.mark.parametrize("kw", [dict(winSize=20), dict(winSize=9, pyrIterations=2), dict(polyN=3, polySigma=0.9),
+                                dict(pyrScale=0.8, pyrLevels=4), dict(pyrScale=0.6, pyrLevels=2, flags=0, winSize=12),
+                                dict(pyrIterations=1), dict(pyrLevels=0), dict(pyrIterations=0, pyrLevels=2)])
+def test_generic_kernel_paths(of, tw, oracle, kw):
+    """Options outside the specialised kernels (window radius not 15/7, polyN not 5/7, pyrScale != 0.5, ...) take the
+    generic kernels; they must match the oracle too."""
+    a, b = tw.synth.make_pair("S", 300, 220, 31, defect=True)
+    rc, fx, fy, _ = of.calculateInternal(a, b, tw.OpticalFlowParameter(**kw))
+    assert rc == 0, of.last_error()
+    ref = oracle.farneback(a, b, FlowParam(**kw))
+    _check_flow(fx, fy, ref, f"{kw}")
+    resp = of.calculate(a, b, tw.OpticalFlowParameter(**kw))
+    status, vec = oracle.sample(ref)
+    assert resp["status"] == status and _vec_pos(resp) == [(v[0], v[1]) for v in vec]
+
+
+def test_kernel_variants_agree(tw, oracle):
+    """The scalar (v1) window kernel, the generic level-image kernel and the tight-pitch layout are alternative code paths
+    for the same arithmetic: all bit-identical to the default path."""
+    a, b = tw.synth.make_pair("S", 480, 300, 33, defect=True)
+    ref = oracle.farneback(a, b, FlowParam())
+    for opt in (None, "gauss_scalar", "level_generic", "tight_pitch"):
+        o = tw.OpticalFlow(0, 480, 300, 1)
+        if opt:
+            o.set_option(opt, 1)
+        rc, fx, fy, _ = o.calculateInternal(a, b)
+        assert rc == 0
+        assert np.array_equal(fx, ref[..., 0]) and np.array_equal(fy, ref[..., 1]), opt
+        o.close()
+
+
 def test_batch_equals_single(of, tw):
     pairs = [tw.synth.make_pair("S", 320, 200, 20 + i, defect=(i % 2 == 0)) for i in range(4)]
     single = [of.calculate(a, b) for a, b in pairs]

@@ -58,7 +58,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
-    int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0;
+    int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_tight_pitch = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -272,7 +272,9 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         s.sigma = (1. / scale - 1) * 0.5;
         s.ksize = std::max(cv_round(s.sigma * 5) | 1, 3);
         s.d.w = cv_round(W * scale); s.d.h = cv_round(H * scale);
-        s.d.pitch = (s.d.w + 31) & ~31;
+        // one row pitch for every level of the plan, a compile-time constant inside the hot kernels (2048 / 4096):
+        // unrolled row addresses become load immediates.  Costs address space, not traffic.
+        s.d.pitch = ctx->opt_tight_pitch ? ((s.d.w + 31) & ~31) : (W <= 2048 ? 2048 : (W <= 4096 ? 4096 : ((W + 31) & ~31)));
         s.d.plane = (size_t)s.d.h * s.d.pitch;
         if (s.ksize > 1023 || s.d.w < 1 || s.d.h < 1) { ctx->err = "unsupported pyramid geometry"; return false; }
         pl.scales.push_back(s);
@@ -821,6 +823,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;
 }
@@ -856,19 +859,27 @@ int tw_debug_read(tw_ctx *ctx, const char *name, int scale, int pair, float *out
     if ((size_t)cn * s.d.w * s.d.h > (size_t)cap_floats) return -2;
     if (w) *w = s.d.w;
     if (h) *h = s.d.h;
-    if (!strcmp(name, "M")) {
-        // M is stored as two float2 planes + one float plane (tw_kernels.cu): de-interleave on the host
+    if (cn == 5) {
+        // R and M are row-interleaved (tw_kernels.cu): (y, c, x) at (y*5 + c)*pitch + x; M additionally packs the
+        // channel pairs (0,1) and (2,3) as float2.  De-interleave on the host.
+        const bool isM = !strcmp(name, "M");
         std::vector<float> tmp(5 * s.d.plane);
         if (cudaMemcpyAsync(tmp.data(), base, sizeof(float) * 5 * s.d.plane, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             return -3;
         const size_t P = (size_t)s.d.w * s.d.h;
+        const int pitch = s.d.pitch;
         for (int y = 0; y < s.d.h; y++)
             for (int x = 0; x < s.d.w; x++) {
-                const size_t o = (size_t)y * s.d.pitch + x, q = (size_t)y * s.d.w + x;
-                out[q] = tmp[2 * o]; out[P + q] = tmp[2 * o + 1];
-                out[2 * P + q] = tmp[2 * s.d.plane + 2 * o]; out[3 * P + q] = tmp[2 * s.d.plane + 2 * o + 1];
-                out[4 * P + q] = tmp[4 * s.d.plane + o];
+                const float *row = tmp.data() + (size_t)y * 5 * pitch;
+                const size_t q = (size_t)y * s.d.w + x;
+                if (isM) {
+                    out[q] = row[2 * x]; out[P + q] = row[2 * x + 1];
+                    out[2 * P + q] = row[2 * pitch + 2 * x]; out[3 * P + q] = row[2 * pitch + 2 * x + 1];
+                    out[4 * P + q] = row[4 * pitch + x];
+                } else {
+                    for (int c = 0; c < 5; c++) out[c * P + q] = row[c * pitch + x];
+                }
             }
         return cn;
     }

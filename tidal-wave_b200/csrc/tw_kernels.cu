@@ -12,6 +12,16 @@ namespace tw {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// base + stride * row as ONE instruction (IMAD.WIDE.U32).  nvcc otherwise strength-reduces the unrolled row
+// addresses into chains of 64-bit adds + LEA pairs: 4 integer instructions per load in kernels whose inner loops
+// are bound by instruction issue.
+__device__ __forceinline__ const char *row_ptr(const char *base, unsigned stride_bytes, unsigned row)
+{
+    unsigned long long out;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(out) : "r"(stride_bytes), "r"(row), "l"(reinterpret_cast<unsigned long long>(base)));
+    return reinterpret_cast<const char *>(out);
+}
+
 __device__ __forceinline__ int reflect101(int p, int len)
 {
     if (len == 1) return 0;
@@ -436,12 +446,12 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float *__restrict__ 
             b6 = b6 + (double)((a1 - m1) * t.xg[k]);
             b5 = b5 + (double)((a2 + m2) * t.g[k]);
         }
-        size_t o = (size_t)gy * pitch + gx;
+        size_t o = (size_t)gy * 5 * pitch + gx; // R is row-interleaved: (y, c, x) at (y*5 + c)*pitch + x
         out[o] = (float)(b3 * t.ig11);
-        out[o + d.plane] = (float)(b2 * t.ig11);
-        out[o + 2 * d.plane] = (float)(b1 * t.ig03 + b5 * t.ig33);
-        out[o + 3 * d.plane] = (float)(b1 * t.ig03 + b4 * t.ig33);
-        out[o + 4 * d.plane] = (float)(b6 * t.ig55);
+        out[o + pitch] = (float)(b2 * t.ig11);
+        out[o + 2 * pitch] = (float)(b1 * t.ig03 + b5 * t.ig33);
+        out[o + 3 * pitch] = (float)(b1 * t.ig03 + b4 * t.ig33);
+        out[o + 4 * pitch] = (float)(b6 * t.ig55);
     }
 }
 
@@ -451,14 +461,14 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float *__restrict__ 
 // The F2F.F64.F32 conversions (3 + 5N per pixel) run on the XU pipe at 16 lanes/clk/SM and bound this kernel.
 constexpr int PF_TW = 96, PF_TH = 16, PF_VW = 112, PF_RV = 8;
 
-template <int N>
+template <int N, int PITCH>
 __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restrict__ I, float *__restrict__ R, LevelDims d, PolyTables t)
 {
     __shared__ float sm[3][PF_TH * PF_VW];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PF_TW, y0 = blockIdx.y * PF_TH;
     const float *img = I + (size_t)blockIdx.z * d.plane;
-    const int w = d.w, h = d.h, pitch = d.pitch;
+    const int w = d.w, h = d.h, pitch = PITCH ? PITCH : d.pitch;
     const bool interior = (y0 - N >= 0) && (y0 + PF_TH + N - 1 <= h - 1); // block-uniform
 
     if (tid < 2 * PF_VW) {
@@ -467,9 +477,13 @@ __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restri
         const int ybase = y0 + g * PF_RV - N;
         float in[PF_RV + 2 * N];
         if (interior) {
-            const float *p = img + (size_t)ybase * pitch + gx;
+            const unsigned rsb = (unsigned)pitch * 4u;
+            const char *p = row_ptr(reinterpret_cast<const char *>(img + gx), rsb, (unsigned)ybase);
 #pragma unroll
-            for (int r = 0; r < PF_RV + 2 * N; r++) in[r] = __ldg(p + (size_t)r * pitch);
+            for (int r = 0; r < PF_RV + 2 * N; r++) {
+                if (PITCH) in[r] = __ldg(reinterpret_cast<const float *>(p) + (size_t)r * PITCH);
+                else in[r] = __ldg(reinterpret_cast<const float *>(row_ptr(p, rsb, (unsigned)r)));
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < PF_RV + 2 * N; r++) in[r] = __ldg(img + (size_t)clampi(ybase + r, 0, h - 1) * pitch + gx);
@@ -530,13 +544,13 @@ __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restri
             res[px][3] = (float)(b1 * t.ig03 + b4 * t.ig33);
             res[px][4] = (float)(b6 * t.ig55);
         }
-        const size_t o = (size_t)gy * pitch + gx;
+        const size_t o = (size_t)gy * 5 * pitch + gx; // row-interleaved R
         if (gx + 1 < w) {
 #pragma unroll
-            for (int c = 0; c < 5; c++) *reinterpret_cast<float2 *>(out + o + c * d.plane) = make_float2(res[0][c], res[1][c]);
+            for (int c = 0; c < 5; c++) *reinterpret_cast<float2 *>(out + o + c * pitch) = make_float2(res[0][c], res[1][c]);
         } else {
 #pragma unroll
-            for (int c = 0; c < 5; c++) out[o + c * d.plane] = res[0][c];
+            for (int c = 0; c < 5; c++) out[o + c * pitch] = res[0][c];
         }
     }
 }
@@ -545,8 +559,15 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 {
     if (t.n == 7 || t.n == 5) {
         dim3 grid((d.w + PF_TW - 1) / PF_TW, (d.h + PF_TH - 1) / PF_TH, nimg);
-        if (t.n == 7) polyexp_fast_kernel<7><<<grid, 256, 0, s>>>(I, R, d, t);
-        else polyexp_fast_kernel<5><<<grid, 256, 0, s>>>(I, R, d, t);
+        if (t.n == 7) {
+            if (d.pitch == 2048) polyexp_fast_kernel<7, 2048><<<grid, 256, 0, s>>>(I, R, d, t);
+            else if (d.pitch == 4096) polyexp_fast_kernel<7, 4096><<<grid, 256, 0, s>>>(I, R, d, t);
+            else polyexp_fast_kernel<7, 0><<<grid, 256, 0, s>>>(I, R, d, t);
+        } else {
+            if (d.pitch == 2048) polyexp_fast_kernel<5, 2048><<<grid, 256, 0, s>>>(I, R, d, t);
+            else if (d.pitch == 4096) polyexp_fast_kernel<5, 4096><<<grid, 256, 0, s>>>(I, R, d, t);
+            else polyexp_fast_kernel<5, 0><<<grid, 256, 0, s>>>(I, R, d, t);
+        }
         return cudaGetLastError();
     }
     dim3 grid((d.w + PE_TW - 1) / PE_TW, (d.h + PE_TH - 1) / PE_TH, nimg);
@@ -562,25 +583,26 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 __device__ __forceinline__ float border_tab(int i) { return i < 2 ? 0.14f : 0.4472f; }
 
 // ------------------------------------------------------------------------------------------------
-// M layout (per pair, 5*plane floats): two float2 planes and one float plane,
-//   [0, 2*plane)        (G11, G12) as float2 [h][pitch]
-//   [2*plane, 4*plane)  (G22, h1)  as float2 [h][pitch]
-//   [4*plane, 5*plane)  h2         as float  [h][pitch]
-// so that the packed f32x2 window kernel loads both channels of a pair with ONE 8-byte load per row (the address
-// arithmetic of two separate planes cost more issue slots than the arithmetic it fed), and writers store float2.
+// R and M are ROW-INTERLEAVED planar (5*plane floats per image / pair): the five channels of image row y are the
+// five consecutive pitch-sized rows (y*5 + c).  With the compile-time pitch every channel, every bilinear neighbour
+// and every row of a register-blocked column is ONE base register + an immediate offset.
+//   R row group: [dy | dx | yy | xx | xy]                     each `pitch` floats
+//   M row group: [(G11,G12) float2 x pitch | (G22,h1) float2 x pitch | h2 float x pitch]   = 5*pitch floats
+// The packed f32x2 window kernel loads both channels of an M pair with one 8-byte load; writers store float2.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_M(float *__restrict__ Mb, size_t plane, size_t o, const float m[5])
+__device__ __forceinline__ void store_M(float *__restrict__ Mb, int pitch, int y, int x, const float m[5])
 {
-    *reinterpret_cast<float2 *>(Mb + 2 * o) = make_float2(m[0], m[1]);
-    *reinterpret_cast<float2 *>(Mb + 2 * plane + 2 * o) = make_float2(m[2], m[3]);
-    Mb[4 * plane + o] = m[4];
+    float *row = Mb + (size_t)y * 5 * pitch;
+    *reinterpret_cast<float2 *>(row + 2 * x) = make_float2(m[0], m[1]);
+    *reinterpret_cast<float2 *>(row + 2 * pitch + 2 * x) = make_float2(m[2], m[3]);
+    row[4 * pitch + x] = m[4];
 }
-// channel c of M as a strided scalar view: element (y, x) is base[(y * pitch + x) * stride]
-__device__ __forceinline__ const float *M_channel(const float *Mb, size_t plane, int c, int &stride)
+// channel c of M as a strided scalar view: element (y, x) is base[(size_t)y * 5 * pitch + x * stride]
+__device__ __forceinline__ const float *M_channel(const float *Mb, int pitch, int c, int &stride)
 {
-    if (c < 4) { stride = 2; return Mb + (size_t)(c >> 1) * 2 * plane + (c & 1); }
+    if (c < 4) { stride = 2; return Mb + (c >> 1) * 2 * pitch + (c & 1); }
     stride = 1;
-    return Mb + 4 * plane;
+    return Mb + 4 * pitch;
 }
 
 // The epilogues are latency-bound, so the 25 loads of a pixel are issued first (upd_load) for several pixels
@@ -592,23 +614,23 @@ struct UpdLoad {
     bool inside;
 };
 
-__device__ __forceinline__ void upd_load(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane, int pitch, int w,
+__device__ __forceinline__ void upd_load(const float *__restrict__ R0, const float *__restrict__ R1, int pitch, int w,
                                          int h, int x, int y, float dx, float dy, UpdLoad &L)
 {
-    const size_t o = (size_t)y * pitch + x;
+    const float *q0 = R0 + (size_t)y * 5 * pitch + x;
     float fx = (float)x + dx, fy = (float)y + dy;
     const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
     L.fx = fx - (float)x1;
     L.fy = fy - (float)y1;
     L.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
 #pragma unroll
-    for (int c = 0; c < 5; c++) L.q[c] = __ldg(R0 + o + c * plane);
+    for (int c = 0; c < 5; c++) L.q[c] = __ldg(q0 + c * pitch);
     if (L.inside) {
-        const float *p = R1 + (size_t)y1 * pitch + x1;
+        const float *p = R1 + (size_t)y1 * 5 * pitch + x1;
 #pragma unroll
         for (int c = 0; c < 5; c++) {
-            L.p[c][0] = __ldg(p); L.p[c][1] = __ldg(p + 1); L.p[c][2] = __ldg(p + pitch); L.p[c][3] = __ldg(p + pitch + 1);
-            p += plane;
+            L.p[c][0] = __ldg(p + c * pitch); L.p[c][1] = __ldg(p + c * pitch + 1);
+            L.p[c][2] = __ldg(p + (5 + c) * pitch); L.p[c][3] = __ldg(p + (5 + c) * pitch + 1);
         }
     }
 }
@@ -649,11 +671,11 @@ __device__ __forceinline__ void upd_compute(const UpdLoad &L, int w, int h, int 
     m[4] = r6 * r2 + r5 * r3;
 }
 
-__device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1, size_t plane,
+__device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1,
                                                    int pitch, int w, int h, int x, int y, float dx, float dy, float m[5])
 {
     UpdLoad L;
-    upd_load(R0, R1, plane, pitch, w, h, x, y, dx, dy, L);
+    upd_load(R0, R1, pitch, w, h, x, y, dx, dy, L);
     upd_compute(L, w, h, x, y, dx, dy, m);
 }
 
@@ -698,8 +720,10 @@ __device__ __forceinline__ void upsample_flow_px(const FirstUpdateArgs &a, int b
     dy = (t0 * gy + t1 * fy) * a.inv_scale;
 }
 
+template <int PITCH>
 __global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
 {
+    if (PITCH) { a.d.pitch = PITCH; a.cd.pitch = PITCH; } // compile-time row pitch: the 4 bilinear neighbours become load immediates
     const int x = blockIdx.x * 32 + threadIdx.x, ya = blockIdx.y * 16 + threadIdx.y, yb = ya + 8;
     if (x >= a.d.w || ya >= a.d.h) return;
     const bool hasb = yb < a.d.h;
@@ -716,15 +740,15 @@ __global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
     if (a.M) {
         const float *R0 = a.R + (size_t)b * 10 * a.d.plane, *R1 = R0 + 5 * a.d.plane;
         UpdLoad La, Lb;
-        upd_load(R0, R1, a.d.plane, a.d.pitch, a.d.w, a.d.h, x, ya, dxa, dya, La);
-        if (hasb) upd_load(R0, R1, a.d.plane, a.d.pitch, a.d.w, a.d.h, x, yb, dxb, dyb, Lb);
+        upd_load(R0, R1, a.d.pitch, a.d.w, a.d.h, x, ya, dxa, dya, La);
+        if (hasb) upd_load(R0, R1, a.d.pitch, a.d.w, a.d.h, x, yb, dxb, dyb, Lb);
         float *M = a.M + (size_t)b * 5 * a.d.plane;
         float m[5];
         upd_compute(La, a.d.w, a.d.h, x, ya, dxa, dya, m);
-        store_M(M, a.d.plane, oa, m);
+        store_M(M, a.d.pitch, ya, x, m);
         if (hasb) {
             upd_compute(Lb, a.d.w, a.d.h, x, yb, dxb, dyb, m);
-            store_M(M, a.d.plane, ob, m);
+            store_M(M, a.d.pitch, yb, x, m);
         }
     }
 }
@@ -732,7 +756,9 @@ __global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a)
 {
     dim3 grid((a.d.w + 31) / 32, (a.d.h + 15) / 16, a.batch);
-    first_update_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
+    if (a.d.pitch == 2048) first_update_kernel<2048><<<grid, dim3(32, 8), 0, s>>>(a);
+    else if (a.d.pitch == 4096) first_update_kernel<4096><<<grid, dim3(32, 8), 0, s>>>(a);
+    else first_update_kernel<0><<<grid, dim3(32, 8), 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -755,15 +781,16 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
     float acc[5][4];
     for (int c = 0; c < 5; c++) {
         int es;
-        const float *Mc = M_channel(Min, plane, c, es);
+        const float *Mc = M_channel(Min, pitch, c, es);
+        const size_t rs = (size_t)5 * pitch;
         for (int i = threadIdx.x; i < SWD * GI_TH; i += blockDim.x) {
             int row = i / SWD, col = i - row * SWD;
             int gy = y0 + row;
             if (gy >= h) continue;
-            int gx = clampi(x0 - m + col, 0, w - 1);
-            float v = Mc[((size_t)gy * pitch + gx) * es] * t.k[0];
+            int gx = clampi(x0 - m + col, 0, w - 1) * es;
+            float v = Mc[gy * rs + gx] * t.k[0];
             for (int k = 1; k <= m; k++)
-                v = v + (Mc[((size_t)min(gy + k, h - 1) * pitch + gx) * es] + Mc[((size_t)max(gy - k, 0) * pitch + gx) * es]) * t.k[k];
+                v = v + (Mc[min(gy + k, h - 1) * rs + gx] + Mc[max(gy - k, 0) * rs + gx]) * t.k[k];
             gi_smem[i] = v;
         }
         __syncthreads();
@@ -790,10 +817,8 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
             f[o] = fx; f[o + plane] = fy;
         } else {
             float mm[5];
-            update_matrices_px(R0, R1, plane, pitch, w, h, x, y, fx, fy, mm);
-            float *M = a.Mout + (size_t)b * 5 * plane;
-#pragma unroll
-            for (int c = 0; c < 5; c++) M[o + c * plane] = mm[c];
+            update_matrices_px(R0, R1, pitch, w, h, x, y, fx, fy, mm);
+            store_M(a.Mout + (size_t)b * 5 * plane, pitch, y, x, mm);
         }
     }
 }
@@ -813,9 +838,9 @@ constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_R
 constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
 
 // phase U of K4/K5: lane = x, coalesced.  Last iteration: write the flow tile; otherwise the next update-matrices.
-__device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *__restrict__ Fb, int tid, int x0, int y0, int b)
+__device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *__restrict__ Fb, int tid, int x0, int y0, int b, int pitch)
 {
-    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const int w = a.d.w, h = a.d.h;
     const size_t plane = a.d.plane;
     if (a.last) {
         float *f = a.flow + (size_t)b * 2 * plane;
@@ -863,14 +888,14 @@ __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *_
             xs[u] = x0 + col; ys[u] = y0 + row;
             ok[u] = xs[u] < w && ys[u] < h;
             fx[u] = Fb[row * GK_FP + col]; fy[u] = Fb[(GK_TH + row) * GK_FP + col];
-            if (ok[u]) upd_load(R0, R1, plane, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
+            if (ok[u]) upd_load(R0, R1, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
         }
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             if (!ok[u]) continue;
             float mm[5];
             upd_compute(L[u], w, h, xs[u], ys[u], fx[u], fy[u], mm);
-            store_M(M, plane, (size_t)ys[u] * pitch + xs[u], mm);
+            store_M(M, pitch, ys[u], xs[u], mm);
         }
     }
 }
@@ -885,8 +910,8 @@ __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, flo
 #pragma unroll 1
     for (int c = 0; c < 5; c++) {
         int es;
-        const float *Mc = M_channel(Min, plane, c, es) + (size_t)gx * es;
-        const size_t rs = (size_t)pitch * es;
+        const float *Mc = M_channel(Min, pitch, c, es) + (size_t)gx * es;
+        const size_t rs = (size_t)pitch * 5;
         float in[GK_RV + 2 * MR];
         if (INTERIOR) {
             const float *p = Mc + (size_t)ybase * rs;
@@ -928,7 +953,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
         for (int i = tid; i < 10 * GK_TH * 3; i += 256) {
             const int pl = i / (GK_TH * 3), rem = i - pl * (GK_TH * 3), row = rem / 3, seg = rem - row * 3;
             const int y = min(y0 + row, h - 1), x = min(x0 + seg * 32, w - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + pl * plane + (size_t)y * pitch + x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl / 5) * 5 * plane + ((size_t)y * 5 + pl % 5) * pitch + x));
         }
     }
 
@@ -980,7 +1005,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     }
     __syncthreads();
 
-    gauss_epilogue(a, Fb, tid, x0, y0, b);
+    gauss_epilogue(a, Fb, tid, x0, y0, b, pitch);
 }
 
 
@@ -1034,20 +1059,27 @@ __device__ __forceinline__ float2 tw_fma2(float2 a, float2 b, float2 c)
 constexpr int G2_P2 = 130, G2_P4 = 132, G2_RV = 8;
 constexpr size_t G2_SMEM = sizeof(float) * (2 * GK_TH * G2_P2 * 2 + GK_TH * G2_P4 + 2 * GK_TH * GK_FP);
 
-template <int MR, bool FMA, bool INTERIOR>
+template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
 __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
                                               int dstride, int ybase, int h, const WinTaps &t)
 {
     constexpr int NIN = G2_RV + 2 * MR;
     const float2 one2 = make_float2(t.one, t.one);
     float2 in[NIN];
+    // one IMAD.WIDE.U32 per load: byte offset = (32-bit row stride in bytes) * (row), added to a 64-bit base
+    const unsigned rsb = (unsigned)rstride * 8u;
+    const char *base = reinterpret_cast<const char *>(src);
     if (INTERIOR) {
-        src += (size_t)ybase * rstride;
+        base = row_ptr(base, rsb, (unsigned)ybase);
 #pragma unroll
-        for (int r = 0; r < NIN; r++) in[r] = __ldg(src + (size_t)r * rstride);
+        for (int r = 0; r < NIN; r++) {
+            if (CPITCH) in[r] = __ldg(reinterpret_cast<const float2 *>(base) + (size_t)r * rstride); // rstride is a constant: immediate offset
+            else in[r] = __ldg(reinterpret_cast<const float2 *>(row_ptr(base, rsb, (unsigned)r)));
+        }
     } else {
 #pragma unroll
-        for (int r = 0; r < NIN; r++) in[r] = __ldg(src + (size_t)clampi(ybase + r, 0, h - 1) * rstride);
+        for (int r = 0; r < NIN; r++)
+            in[r] = __ldg(reinterpret_cast<const float2 *>(row_ptr(base, rsb, (unsigned)clampi(ybase + r, 0, h - 1))));
     }
 #pragma unroll
     for (int o = 0; o < G2_RV; o++) {
@@ -1067,7 +1099,7 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
 // (column pair jj, row group g) -- every item is "38 8-byte loads, 8 packed outputs".  Columns are replicated by
 // clamping the address; the h2 column pair is clamped as a pair (x0 and w are even multiples of the tile / pitch
 // except at the right edge, where both columns clamp to w-1 via the scalar fallback).
-template <int MR, bool FMA, bool INTERIOR>
+template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
 __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, float *__restrict__ sm, const WinTaps &t, int tid, int x0,
                                                int y0, int w, int h, int pitch, size_t plane)
 {
@@ -1078,17 +1110,17 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
     for (int it = 0; it < 4; it++) {
         const int pair = it >> 1, j = tid & 127, g = (tid >> 7) + 2 * (it & 1);
         const int gx = clampi(x0 - 16 + j, 0, w - 1);
-        const float2 *src = reinterpret_cast<const float2 *>(Min + (size_t)pair * 2 * plane) + gx;
+        const float2 *src = reinterpret_cast<const float2 *>(Min + pair * 2 * pitch) + gx;
         float2 *dst = (pair ? P23 : P01) + g * G2_RV * G2_P2 + j;
-        gauss_v_item2<MR, FMA, INTERIOR>(src, pitch, dst, G2_P2, y0 + g * G2_RV - MR, h, t);
+        gauss_v_item2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 + g * G2_RV - MR, h, t);
     }
     {
         const int jj = tid & 63, g = tid >> 6;
         const int xa = x0 - 16 + 2 * jj;
         float2 *dst = P4 + g * G2_RV * (G2_P4 / 2) + jj;
-        const float *P = Min + 4 * plane;
+        const float *P = Min + 4 * pitch;
         if (xa >= 0 && xa + 1 <= w - 1) {
-            gauss_v_item2<MR, FMA, INTERIOR>(reinterpret_cast<const float2 *>(P + xa), pitch / 2, dst, G2_P4 / 2, y0 + g * G2_RV - MR, h, t);
+            gauss_v_item2<MR, FMA, INTERIOR, CPITCH>(reinterpret_cast<const float2 *>(P + xa), 5 * pitch / 2, dst, G2_P4 / 2, y0 + g * G2_RV - MR, h, t);
         } else { // edge column pair: clamp each column separately (scalar loads)
             const int ca = clampi(xa, 0, w - 1), cb = clampi(xa + 1, 0, w - 1), ybase = y0 + g * G2_RV - MR;
             constexpr int NIN = G2_RV + 2 * MR;
@@ -1096,7 +1128,7 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
             float2 in[NIN];
 #pragma unroll
             for (int r = 0; r < NIN; r++) {
-                const size_t o = (size_t)clampi(ybase + r, 0, h - 1) * pitch;
+                const size_t o = (size_t)clampi(ybase + r, 0, h - 1) * 5 * pitch;
                 in[r] = make_float2(__ldg(P + o + ca), __ldg(P + o + cb));
             }
 #pragma unroll
@@ -1115,14 +1147,16 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
     }
 }
 
-template <int MR, bool FMA>
+// PITCH > 0: the row pitch is a compile-time constant (the plan pads every level to 2048 or 4096 floats), so the
+// unrolled row addresses become LDG immediates instead of 3-4 integer instructions per load.
+template <int MR, bool FMA, int PITCH>
 __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps t)
 {
     extern __shared__ __align__(16) float gk_smem[];
     float *Fb = gk_smem + 2 * GK_TH * G2_P2 * 2 + GK_TH * G2_P4;
     const int tid = threadIdx.x, lane = tid & 31;
     const int x0 = blockIdx.x * GK_TW, y0 = blockIdx.y * GK_TH, b = blockIdx.z;
-    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const int w = a.d.w, h = a.d.h, pitch = PITCH ? PITCH : a.d.pitch;
     const size_t plane = a.d.plane;
     const float *Min = a.Min + (size_t)b * 5 * plane;
 
@@ -1136,8 +1170,9 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
             const int row = i / NL, seg = i - row * NL;
             const int y = clampi(y0 - MR + row, 0, h - 1);
             const float *p;
-            if (seg < 16) p = Min + (size_t)(seg >> 3) * 2 * plane + ((size_t)y * pitch + min(xl + (seg & 7) * 16, w - 1)) * 2;
-            else p = Min + 4 * plane + (size_t)y * pitch + min(xl + (seg - 16) * 32, w - 1);
+            const float *rowp = Min + (size_t)y * 5 * pitch;
+            if (seg < 16) p = rowp + (seg >> 3) * 2 * pitch + min(xl + (seg & 7) * 16, w - 1) * 2;
+            else p = rowp + 4 * pitch + min(xl + (seg - 16) * 32, w - 1);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
     }
@@ -1146,15 +1181,15 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
         for (int i = tid; i < 10 * GK_TH * 3; i += 256) {
             const int pl = i / (GK_TH * 3), rem = i - pl * (GK_TH * 3), row = rem / 3, seg = rem - row * 3;
             const int y = min(y0 + row, h - 1), x = min(x0 + seg * 32, w - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + pl * plane + (size_t)y * pitch + x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl / 5) * 5 * plane + ((size_t)y * 5 + pl % 5) * pitch + x));
         }
     }
 
     // ---- phase V (packed) ----
     if ((y0 - MR >= 0) && (y0 + GK_TH + MR - 1 <= h - 1))
-        gauss_v_phase2<MR, FMA, true>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+        gauss_v_phase2<MR, FMA, true, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
     else
-        gauss_v_phase2<MR, FMA, false>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+        gauss_v_phase2<MR, FMA, false, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
     __syncthreads();
 
     // ---- phase H (packed) + solve ----
@@ -1226,21 +1261,29 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
         }
     }
     __syncthreads();
-    gauss_epilogue(a, Fb, tid, x0, y0, b);
+    gauss_epilogue(a, Fb, tid, x0, y0, b, pitch);
+}
+
+template <int MR, bool FMA, int PITCH>
+static cudaError_t launch_gauss_fast2p(cudaStream_t s, const IterArgs &a, const WinTaps &t)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
+    gauss_iter2_kernel<MR, FMA, PITCH><<<grid, 256, G2_SMEM, s>>>(a, t);
+    return cudaGetLastError();
 }
 
 template <int MR, bool FMA>
 static cudaError_t launch_gauss_fast2(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
-    gauss_iter2_kernel<MR, FMA><<<grid, 256, G2_SMEM, s>>>(a, t);
-    return cudaGetLastError();
+    if (a.d.pitch == 2048) return launch_gauss_fast2p<MR, FMA, 2048>(s, a, t);
+    if (a.d.pitch == 4096) return launch_gauss_fast2p<MR, FMA, 4096>(s, a, t);
+    return launch_gauss_fast2p<MR, FMA, 0>(s, a, t);
 }
 
 template <int MR, bool FMA>
@@ -1287,9 +1330,9 @@ __global__ void __launch_bounds__(128) box_vsum_kernel(const float *__restrict__
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= d.w) return;
     int es;
-    const float *M = M_channel(Min + (size_t)(blockIdx.y / 5) * 5 * d.plane, d.plane, blockIdx.y % 5, es) + (size_t)x * es;
+    const float *M = M_channel(Min + (size_t)(blockIdx.y / 5) * 5 * d.plane, d.pitch, blockIdx.y % 5, es) + (size_t)x * es;
     double *v = VT + (size_t)blockIdx.y * planeT + (size_t)x * pitchT;
-    const int h = d.h, pitch = d.pitch * es;
+    const int h = d.h, pitch = d.pitch * 5;
     double vs = (double)(M[0] * (float)(m + 2));
     for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * pitch];
 #pragma unroll 4
