@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -242,8 +242,16 @@ def main():
     achieved = tv["alg_bytes"] / (tv["ms"] * 1e-3) / 1e9
     kernel_ms_total = sum(v["ms"] for v in fams.values())
     alg_total = sum(v["alg_bytes"] for v in fams.values())
+    # DRAM traffic per launch of that family from the committed ncu --set full capture (same command line, same batch)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1g_traffic.json")))
+        if tj.get("batch") == B and top in tj:
+            traffic = tj[top]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": tv["ms"] / tv["launches"],
+                "traffic": traffic, "traffic_source": "profiles/r1g_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None, "peak_source": peak_src, "avg_launch_ms": tv["ms"] / tv["launches"],
                 "alg_bytes_per_launch": tv["alg_bytes"] / tv["launches"], "share_of_step": tv["ms"] / kernel_ms_total,
                 "pipeline": {"alg_bytes_per_pair": alg_total / (B * args.steps), "achieved": alg_total / (elapsed_ms * 1e-3) / 1e9,
                              "frac": alg_total / (elapsed_ms * 1e-3) / 1e9 / peak},

@@ -101,6 +101,26 @@ class RefOracle:
         self.lib.twref_resize_linear(_fp(src), W, H, cn, _fp(out), w, h)
         return out
 
+    def resize_u8(self, img, w, h):
+        """The +-5 px path of OpticalFlow::calculate (/root/reference/src/opticalflow.cpp:64-68): cv::resize, INTER_LINEAR."""
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        out = np.empty((h, w), np.uint8)
+        self.lib.twref_resize_u8(img.ctypes.data_as(C.c_void_p), W, H, W, out.ctypes.data_as(C.c_void_p), w, h, w)
+        return out
+
+    def calculate(self, expect, target, p: "FlowParam" = None, span=10, threshold=5.0):
+        """OpticalFlow::calculate + Consumer::run on decoded images (/root/reference/src/opticalflow.cpp:52-73,
+        src/consumer.cpp:59-88) -> (status, vectors, flow or None)."""
+        p = p or FlowParam()
+        if abs(expect.shape[0] - target.shape[0]) > 5 or abs(expect.shape[1] - target.shape[1]) > 5:
+            return "ERROR", [], None
+        if expect.shape != target.shape:
+            target = self.resize_u8(target, expect.shape[1], expect.shape[0])
+        flow = self.farneback(expect, target, p)
+        status, vec = self.sample(flow, span, threshold)
+        return status, vec, flow
+
     def polyexp_tables(self, n, sigma):
         g = np.zeros(65, np.float32); xg = np.zeros(65, np.float32); xxg = np.zeros(65, np.float32)
         ig = np.zeros(4, np.float64)

@@ -159,6 +159,7 @@ def test_error_codes(of, tw):
     a = np.zeros((100, 120), np.uint8)
     r = of.calculate(a, np.zeros((100, 126), np.uint8))
     assert r["status"] == "ERROR" and r["code"] == 3 and r["reason"] == "Don't match image size"
+    assert of.calculate(a, np.zeros((100, 125), np.uint8))["status"] != "ERROR"  # within 5 px: resized, not an error
     r = of.calculate(a, np.zeros((106, 120), np.uint8))
     assert r["code"] == 3
     r = of.calculate(None, a)
@@ -170,6 +171,22 @@ def test_error_codes(of, tw):
         assert r["status"] == "ERROR" and r["code"] == 1, bad
     # the context survives errors
     assert of.calculate(a, a)["status"] == "OK"
+
+
+@pytest.mark.parametrize("dw,dh", [(5, 0), (0, -5), (3, 4), (-2, -5), (-5, 5), (1, -1)])
+def test_size_tolerance_resize_path(of, tw, oracle, dw, dh):
+    """src/opticalflow.cpp:52-68: sizes within 5 px -> the target is bilinearly resized to the expected size first."""
+    a, b0 = tw.synth.make_pair("S", 320, 200, 41, defect=True)
+    rng = np.random.default_rng(5)
+    b = rng.integers(0, 256, (200 + dh, 320 + dw), dtype=np.uint8)
+    h0, w0 = min(200, 200 + dh), min(320, 320 + dw)
+    b[:h0, :w0] = b0[:h0, :w0]
+    resp = of.calculate(a, b)
+    status, vec, flow = oracle.calculate(a, b)
+    assert resp["status"] == status and (resp["height"], resp["width"]) == (200, 320)
+    assert _vec_pos(resp) == [(v[0], v[1]) for v in vec]
+    for v, g in zip(resp["vector"], vec):
+        assert v["dx"] == g[2] and v["dy"] == g[3]
 
 
 def test_vector_cap_truncates(of, golden):

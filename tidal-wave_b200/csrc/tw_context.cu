@@ -75,6 +75,8 @@ struct tw_ctx {
     int fam_launches[F_COUNT] = {0};
     double fam_bytes[F_COUNT] = {0};
     long long launches = 0;
+    void *rs_buf = nullptr; // +-5 px resize path: raw target + coefficient tables
+    size_t rs_cap = 0;
     void *flush_buf = nullptr;
     int flush_val = 0;
     std::string err;
@@ -124,8 +126,10 @@ bool dev_upload(tw_ctx *ctx, T **out, const std::vector<T> &v)
     return true;
 }
 
-// per-axis bilinear coefficients (double expression, one cast).
-void resize_coeffs(int N, int n, std::vector<int> &idx, std::vector<float> &frac)
+// per-axis bilinear coefficients (double expression, one cast).  OpenCV clamps an out-of-range
+// tap along x (index clamped, fraction zeroed) but along y keeps the fraction and only clips the two row indices;
+// the two rules differ in the first / last output row of an up-scale (the flow up-sample, the +-5 px target resize).
+void resize_coeffs(int N, int n, std::vector<int> &idx, std::vector<float> &frac, bool clamp_fraction = true)
 {
     idx.resize(n); frac.resize(n);
     double s = 1.0 / (n / (double)N);
@@ -133,9 +137,23 @@ void resize_coeffs(int N, int n, std::vector<int> &idx, std::vector<float> &frac
         float f = (float)((d + 0.5) * s - 0.5);
         int i = (int)floorf(f);
         f = f - (float)i;
-        if (i < 0) { f = 0; i = 0; }
-        if (i >= N - 1) { f = 0; i = N - 1; }
+        if (clamp_fraction) {
+            if (i < 0) { f = 0; i = 0; }
+            if (i >= N - 1) { f = 0; i = N - 1; }
+        }
         idx[d] = i; frac[d] = f;
+    }
+}
+
+// OpenCV 8-bit bilinear coefficients: the float fractions scaled by 2048 and rounded half-to-even (saturate_cast<short>).
+void resize_coeffs_u8(int N, int n, std::vector<int> &idx, std::vector<short> &alpha, bool clamp_fraction)
+{
+    std::vector<float> frac;
+    resize_coeffs(N, n, idx, frac, clamp_fraction);
+    alpha.resize(2 * (size_t)n);
+    for (int d = 0; d < n; d++) {
+        alpha[2 * d] = (short)nearbyintf((1.f - frac[d]) * 2048.f);
+        alpha[2 * d + 1] = (short)nearbyintf(frac[d] * 2048.f);
     }
 }
 
@@ -332,7 +350,7 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         if (si > 0) {
             const Scale &cs = pl.scales[si - 1];
             resize_coeffs(cs.d.w, s.d.w, xi, xf);
-            resize_coeffs(cs.d.h, s.d.h, yi, yf);
+            resize_coeffs(cs.d.h, s.d.h, yi, yf, false); // rows: fraction kept, indices clipped by the kernel
             if (!dev_upload(ctx, &s.up_xi, xi) || !dev_upload(ctx, &s.up_xf, xf) || !dev_upload(ctx, &s.up_yi, yi) ||
                 !dev_upload(ctx, &s.up_yf, yf))
                 return false;
@@ -563,6 +581,7 @@ void tw_destroy(tw_ctx *ctx)
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->d_vectors) cudaFree(ctx->d_vectors);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->rs_buf) cudaFree(ctx->rs_buf);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->ev_r0) cudaEventDestroy(ctx->ev_r0);
@@ -611,6 +630,43 @@ static int upload_impl(tw_ctx *ctx, int n, const uint8_t *const *expect, const u
         if (e != cudaSuccess) { set_err(ctx, "H2D", e); return TW_CUDA_ERROR; }
     }
     return TW_OK;
+}
+
+// Uploads a (tw x th) target and resizes it on the device into the target slot of pair 0 (plan already built).
+static bool upload_resized_target(tw_ctx *ctx, const uint8_t *target, int tw_, int th_, int ew, int eh)
+{
+    Plan &pl = ctx->plan;
+    const int tp = (tw_ + 15) & ~15;
+    size_t need = (size_t)tp * th_ + sizeof(int) * (ew + eh) + sizeof(short) * 2 * (ew + eh) + 1024;
+    if (ctx->rs_cap < need) {
+        if (ctx->rs_buf) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->rs_buf); ctx->rs_buf = nullptr; }
+        cudaError_t e = cudaMalloc(&ctx->rs_buf, need);
+        if (e != cudaSuccess) return set_err(ctx, "cudaMalloc", e);
+        ctx->rs_cap = need;
+    }
+    std::vector<int> xi, yi; std::vector<short> xa, ya;
+    resize_coeffs_u8(tw_, ew, xi, xa, true);
+    resize_coeffs_u8(th_, eh, yi, ya, false);
+    uint8_t *base = reinterpret_cast<uint8_t *>(ctx->rs_buf);
+    uint8_t *d_img = base;
+    size_t off = ((size_t)tp * th_ + 255) & ~(size_t)255;
+    int *d_xi = reinterpret_cast<int *>(base + off); off += sizeof(int) * ew;
+    int *d_yi = reinterpret_cast<int *>(base + off); off += sizeof(int) * eh;
+    short *d_xa = reinterpret_cast<short *>(base + off); off += sizeof(short) * 2 * ew;
+    short *d_ya = reinterpret_cast<short *>(base + off);
+    CK(cudaMemcpy2DAsync(d_img, tp, target, tw_, tw_, th_, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xi, xi.data(), sizeof(int) * ew, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_yi, yi.data(), sizeof(int) * eh, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xa, xa.data(), sizeof(short) * 2 * ew, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ya, ya.data(), sizeof(short) * 2 * eh, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // the tables are host temporaries
+    ResizeU8Args ra{};
+    ra.src = d_img; ra.W = tw_; ra.H = th_; ra.spitch = tp;
+    ra.dst = pl.src + (size_t)eh * pl.spitch; ra.w = ew; ra.h = eh; ra.dpitch = pl.spitch;
+    ra.xi = d_xi; ra.yi = d_yi; ra.xa = d_xa; ra.ya = d_ya;
+    ctx->launches++;
+    CK(launch_resize_u8(ctx->stream, ra));
+    return true;
 }
 
 int tw_batch_upload(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride)
@@ -748,7 +804,14 @@ int tw_compare(tw_ctx *ctx, const uint8_t *expect, int ew, int eh, const uint8_t
     // src/opticalflow.cpp:52-61
     if (abs(eh - th_) > 5 || abs(ew - tw_) > 5) { fill_error(res, TW_DONT_MATCH_SIZE, "Don't match image size"); return res->code; }
     if (eh != th_ || ew != tw_) {
-        fill_error(res, TW_UNSUPPORTED, "size differs within 5 px: device resize of the target not implemented yet");
+        // src/opticalflow.cpp:64-68: sizes within 5 px -> the target is resized (bilinear) to the expected size
+        if (span < 1) { fill_error(res, TW_BAD_PARAMETER, "span must be >= 1"); return res->code; }
+        if (validate_param(param) != TW_OK) { fill_error(res, TW_BAD_PARAMETER, "bad optical-flow parameter"); return res->code; }
+        int rc = upload_impl(ctx, 1, &expect, &expect, ew, eh, ew, param); // builds the plan, fills the expected slot
+        if (rc == TW_OK && !upload_resized_target(ctx, target, tw_, th_, ew, eh)) rc = TW_CUDA_ERROR;
+        if (rc == TW_OK) rc = tw_batch_run(ctx, 1, ew, eh, param, threshold, span);
+        if (rc != TW_OK) { fill_error(res, rc, ctx->err.c_str()); return res->code; }
+        tw_batch_fetch(ctx, 1, out, cap, res);
         return res->code;
     }
     tw_compare_batch(ctx, 1, &expect, &target, ew, eh, ew, param, threshold, span, out, cap, res);

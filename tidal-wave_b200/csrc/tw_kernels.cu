@@ -708,7 +708,8 @@ __device__ __forceinline__ void upsample_flow_px(const FirstUpdateArgs &a, int b
     }
     if (!a.coarse) return;
     const float *cf = a.coarse + (size_t)b * 2 * a.cd.plane;
-    const int x0 = __ldg(a.xi + x), x1 = min(x0 + 1, a.cd.w - 1), y0 = __ldg(a.yi + y), y1 = min(y0 + 1, a.cd.h - 1);
+    const int x0 = __ldg(a.xi + x), x1 = min(x0 + 1, a.cd.w - 1);
+    const int sy = __ldg(a.yi + y), y0 = clampi(sy, 0, a.cd.h - 1), y1 = clampi(sy + 1, 0, a.cd.h - 1); // rows clipped, fraction kept
     const float fx = __ldg(a.xf + x), gx = 1.f - fx, fy = __ldg(a.yf + y), gy = 1.f - fy;
     const float *r0 = cf + (size_t)y0 * a.cd.pitch, *r1 = cf + (size_t)y1 * a.cd.pitch;
     const float a00 = __ldg(r0 + x0), a01 = __ldg(r0 + x1), a10 = __ldg(r1 + x0), a11 = __ldg(r1 + x1);
@@ -721,41 +722,31 @@ __device__ __forceinline__ void upsample_flow_px(const FirstUpdateArgs &a, int b
 }
 
 template <int PITCH>
-__global__ void __launch_bounds__(256) first_update_kernel(FirstUpdateArgs a)
+__global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
 {
+    // one pixel per thread and <= 42 registers: 48 warps / SM keep enough loads in flight for this HBM-latency-bound
+    // kernel (measured: two pixels per thread at 78 registers was 15 % slower).
     if (PITCH) { a.d.pitch = PITCH; a.cd.pitch = PITCH; } // compile-time row pitch: the 4 bilinear neighbours become load immediates
-    const int x = blockIdx.x * 32 + threadIdx.x, ya = blockIdx.y * 16 + threadIdx.y, yb = ya + 8;
-    if (x >= a.d.w || ya >= a.d.h) return;
-    const bool hasb = yb < a.d.h;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.d.w || y >= a.d.h) return;
     const int b = blockIdx.z;
-    float dxa, dya, dxb = 0.f, dyb = 0.f;
-    upsample_flow_px(a, b, x, ya, dxa, dya);
-    if (hasb) upsample_flow_px(a, b, x, yb, dxb, dyb);
-    const size_t oa = (size_t)ya * a.d.pitch + x, ob = (size_t)yb * a.d.pitch + x;
+    float dx, dy;
+    upsample_flow_px(a, b, x, y, dx, dy);
     if (a.flow_out) {
-        float *f = a.flow_out + (size_t)b * 2 * a.d.plane;
-        f[oa] = dxa; f[oa + a.d.plane] = dya;
-        if (hasb) { f[ob] = dxb; f[ob + a.d.plane] = dyb; }
+        float *f = a.flow_out + (size_t)b * 2 * a.d.plane + (size_t)y * a.d.pitch + x;
+        f[0] = dx; f[a.d.plane] = dy;
     }
     if (a.M) {
         const float *R0 = a.R + (size_t)b * 10 * a.d.plane, *R1 = R0 + 5 * a.d.plane;
-        UpdLoad La, Lb;
-        upd_load(R0, R1, a.d.pitch, a.d.w, a.d.h, x, ya, dxa, dya, La);
-        if (hasb) upd_load(R0, R1, a.d.pitch, a.d.w, a.d.h, x, yb, dxb, dyb, Lb);
-        float *M = a.M + (size_t)b * 5 * a.d.plane;
         float m[5];
-        upd_compute(La, a.d.w, a.d.h, x, ya, dxa, dya, m);
-        store_M(M, a.d.pitch, ya, x, m);
-        if (hasb) {
-            upd_compute(Lb, a.d.w, a.d.h, x, yb, dxb, dyb, m);
-            store_M(M, a.d.pitch, yb, x, m);
-        }
+        update_matrices_px(R0, R1, a.d.pitch, a.d.w, a.d.h, x, y, dx, dy, m);
+        store_M(a.M + (size_t)b * 5 * a.d.plane, a.d.pitch, y, x, m);
     }
 }
 
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a)
 {
-    dim3 grid((a.d.w + 31) / 32, (a.d.h + 15) / 16, a.batch);
+    dim3 grid((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.batch);
     if (a.d.pitch == 2048) first_update_kernel<2048><<<grid, dim3(32, 8), 0, s>>>(a);
     else if (a.d.pitch == 4096) first_update_kernel<4096><<<grid, dim3(32, 8), 0, s>>>(a);
     else first_update_kernel<0><<<grid, dim3(32, 8), 0, s>>>(a);
@@ -1404,6 +1395,32 @@ cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, cons
     const int pitchT = (d.h + 31) & ~31;
     dim3 grid((d.h + 127) / 128, batch);
     box_hscan_kernel<<<grid, 128, 0, s>>>(VT, flow, d, m, 1. / ((double)winSize * winSize), pitchT, (size_t)d.w * pitchT);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Size-tolerance path of OpticalFlow::calculate (/root/reference/src/opticalflow.cpp:64-68): cv::resize of the
+// 8-bit target to the expected size, INTER_LINEAR in effect.  OpenCV's fixed-point bilinear: 11-bit coefficients,
+// horizontal pass in int, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+// Tables: xi/xa clamped along x; yi/ya with the fraction kept and the row indices clipped (see resize_coeffs).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_u8_kernel(ResizeU8Args a)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    const int sy = a.yi[y], y0 = clampi(sy, 0, a.H - 1), y1 = clampi(sy + 1, 0, a.H - 1);
+    const int x0 = a.xi[x], x1 = min(x0 + 1, a.W - 1);
+    const int a0 = a.xa[2 * x], a1 = a.xa[2 * x + 1], b0 = a.ya[2 * y], b1 = a.ya[2 * y + 1];
+    const uint8_t *s0 = a.src + (size_t)y0 * a.spitch, *s1 = a.src + (size_t)y1 * a.spitch;
+    const int r0 = s0[x0] * a0 + s0[x1] * a1, r1 = s1[x0] * a0 + s1[x1] * a1;
+    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    a.dst[(size_t)y * a.dpitch + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+cudaError_t launch_resize_u8(cudaStream_t s, const ResizeU8Args &a)
+{
+    dim3 grid((a.w + 31) / 32, (a.h + 7) / 8);
+    resize_u8_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -96,6 +96,15 @@ cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &
 cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *VT, const LevelDims &d, int batch, int m);
 cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, const LevelDims &d, int batch, int m, int winSize);
 
+// +-5 px size-tolerance path: OpenCV's 8-bit fixed-point bilinear resize of the target to the expected size.
+struct ResizeU8Args {
+    const uint8_t *src; int W, H, spitch;   // device, target as uploaded
+    uint8_t *dst; int w, h, dpitch;         // device, target slot of the pair
+    const int *xi, *yi;                     // device tables
+    const short *xa, *ya;                   // device, 2 coefficients per output column / row (x2048)
+};
+cudaError_t launch_resize_u8(cudaStream_t s, const ResizeU8Args &a);
+
 // Span sampling + threshold classification + ordered compaction, reference src/consumer.cpp:60-77.
 struct SampleArgs {
     const float *flow; // [B][2] planes, full-res
