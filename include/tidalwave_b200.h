@@ -99,6 +99,10 @@ int tw_compare(tw_ctx *ctx, const uint8_t *expect, int ew, int eh, const uint8_t
                const tw_flow_param *param, double threshold, int span, tw_vector *out, int cap,
                tw_result *res);
 
+/* The resize step of OpticalFlow::calculate alone (src/opticalflow.cpp:64-68, cv::resize INTER_LINEAR on 8-bit data), for
+ * hosts that keep calculate() / calculateInternal() separate: target (tw x th) -> out (ew x eh), tightly packed. */
+int tw_resize_target(tw_ctx *ctx, const uint8_t *target, int tw, int th, uint8_t *out, int ew, int eh);
+
 /* n same-size pairs through one batched launch sequence (n <= max_batch).  out has n*cap entries
  * (pair i at out + i*cap), res has n entries.  Semantics per pair identical to tw_compare. */
 int tw_compare_batch(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w,

@@ -833,6 +833,21 @@ int tw_l2_flush(tw_ctx *ctx)
     return TW_OK;
 }
 
+int tw_resize_target(tw_ctx *ctx, const uint8_t *target, int tw_, int th_, uint8_t *out, int ew, int eh)
+{
+    if (!ctx || !target || !out || tw_ < 1 || th_ < 1 || ew < 1 || eh < 1) return TW_BAD_PARAMETER;
+    cudaSetDevice(ctx->device);
+    tw_flow_param p;
+    if (ctx->plan.valid) p = ctx->plan.p; else tw_default_param(&p);
+    if (!build_plan(ctx, ew, eh, p)) return TW_CUDA_ERROR;
+    if (!upload_resized_target(ctx, target, tw_, th_, ew, eh)) return TW_CUDA_ERROR;
+    Plan &pl = ctx->plan;
+    cudaError_t e = cudaMemcpy2DAsync(out, ew, pl.src + (size_t)eh * pl.spitch, pl.spitch, ew, eh, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "resize D2H", e); return TW_CUDA_ERROR; }
+    return TW_OK;
+}
+
 int tw_timer_start(tw_ctx *ctx)
 {
     if (!ctx) return TW_BAD_PARAMETER;
