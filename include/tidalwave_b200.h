@@ -76,6 +76,11 @@ const char *tw_version(void);
 /* Number of CUDA devices visible (cv::gpu::getCudaEnabledDeviceCount, src/consumer.cpp:19-20). */
 int tw_device_count(void);
 
+/* cv::imread(path, IMREAD_GRAYSCALE) on an in-memory file (src/opticalflow.cpp:37,44): PNG (non-interlaced, 8-bit; colour ->
+ * gray exactly as OpenCV/libpng: (9797 R + 19234 G + 3737 B) >> 15) and binary PGM.  Host code, no device needed.  Call with
+ * out == NULL to query *w, *h.  Anything else (JPEG, ...) -> TW_BAD_IMAGE_FORMAT, reported by callers as "Can't open <path>". */
+int tw_decode_gray(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap, int *w, int *h);
+
 /* ---- operator seam: OpticalFlow instance, one per consumer thread (src/consumer.cpp:27-35) ----
  * A context is thread-confined, bound to one device (cv::gpu::setDevice(id), src/consumer.cpp:22),
  * owns all device memory, pinned staging and its stream.  max_batch = pairs processed per launch

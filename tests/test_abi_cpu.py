@@ -61,3 +61,31 @@ def test_synth_is_deterministic(tw):
     a1, b1 = tw.synth.make_pair("S", 160, 120, 5, defect=True)
     a2, b2 = tw.synth.make_pair("S", 160, 120, 5, defect=True)
     assert np.array_equal(a1, a2) and np.array_equal(b1, b2) and a1.dtype == np.uint8 and not np.array_equal(a1, b1)
+
+
+def test_decode_gray_matches_cv2_fixtures(tw):
+    """tw_decode_gray (row f-1): PNG colour types 0/2/3/6 -> gray bit-identical to cv2.imread(IMREAD_GRAYSCALE) (goldens made by
+    tools; the two fixture PNGs are the reference's own test files); JPEG and junk are 'empty images'."""
+    import glob
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    n = 0
+    for png in sorted(glob.glob(os.path.join(gold, "png", "*.png"))):
+        ref = png[:-4] + ".gray.npy"
+        img = tw.imread_gray(png)
+        assert img is not None and img.dtype == np.uint8
+        if os.path.exists(ref):
+            assert np.array_equal(img, np.load(ref)), png
+            n += 1
+    assert n >= 5
+    assert np.array_equal(tw.imread_gray(os.path.join(gold, "png", "fixture_s2_expected.png")), np.load(os.path.join(gold, "fixture_s2_expected.npy")))
+    assert np.array_equal(tw.imread_gray(os.path.join(gold, "png", "fixture_s2_revision2.png")), np.load(os.path.join(gold, "fixture_s2_revision2.npy")))
+    assert tw.imread_gray("/nonexistent/file.png") is None
+
+
+def test_decode_pgm_roundtrip(tw, tmp_path):
+    img = (np.arange(37 * 53) % 251).astype(np.uint8).reshape(37, 53)
+    p = tmp_path / "a.pgm"
+    p.write_bytes(b"P5\n# comment\n53 37\n255\n" + img.tobytes())
+    assert np.array_equal(tw.imread_gray(str(p)), img)
+    (tmp_path / "b.jpg").write_bytes(b"\xff\xd8\xff\xe0junk")
+    assert tw.imread_gray(str(tmp_path / "b.jpg")) is None

@@ -7,6 +7,7 @@ OK / SUSPICIOUS / ERROR).  The directory name carries a hyphen (the reference's 
 Contents: csrc/ (sm_100a CUDA kernels + C ABI + dispatcher), api.py (ctypes binding + mirror of the reference's
 operator interface), synth.py (seeded synthetic screenshot pairs).
 """
-from . import dist, synth  # noqa: F401
-from .api import (LIB_PATH, OpticalFlow, OpticalFlowParameter, Pool, declared_symbols, load, tw_flow_param,  # noqa: F401
+from . import dist, synth, tidalwave  # noqa: F401
+from .tidalwave import TidalWave, create, run  # noqa: F401
+from .api import (LIB_PATH, imread_gray, OpticalFlow, OpticalFlowParameter, Pool, declared_symbols, load, tw_flow_param,  # noqa: F401
                   tw_result, tw_vector)

@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     L.tw_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(tw_flow_param), C.c_double, C.c_int]
     L.tw_batch_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(tw_vector), C.c_int, C.POINTER(tw_result)]
     L.tw_resize_target.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.tw_decode_gray.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tw_sync.argtypes = [C.c_void_p]
     L.tw_batch_flow.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.tw_host_alloc.restype = C.c_void_p
@@ -121,6 +122,23 @@ def declared_symbols() -> list[str]:
     src = open(HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(tw_[a-z0-9_]+)\s*\(", src)))
+
+
+def imread_gray(path: str):
+    """cv::imread(path, IMREAD_GRAYSCALE) (/root/reference/src/opticalflow.cpp:37,44) through tw_decode_gray: PNG / PGM.
+    Returns None (an "empty Mat") for a missing file or a format this build cannot decode bit-exactly (JPEG)."""
+    try:
+        data = open(path, "rb").read()
+    except OSError:
+        return None
+    L = load()
+    w = C.c_int(); h = C.c_int()
+    if not data or L.tw_decode_gray(data, len(data), None, 0, C.byref(w), C.byref(h)) != 0:
+        return None
+    out = np.empty((h.value, w.value), np.uint8)
+    if L.tw_decode_gray(data, len(data), out.ctypes.data, out.size, C.byref(w), C.byref(h)) != 0:
+        return None
+    return out
 
 
 def _u8(img) -> np.ndarray:

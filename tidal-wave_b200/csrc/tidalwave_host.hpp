@@ -9,7 +9,7 @@
 //   Observer<Response, std::string, Report>                     /root/reference/src/observer.h:10-18
 //
 // cv::Mat is replaced by two plain containers (Image = CV_8UC1, Plane = CV_32FC1); cv::imread by imread_gray()
-// (binary PGM only -- PNG/JPEG decoding is SURVEY row f-1).  uv_thread / uv_mutex / uv_cond become std::thread /
+// (PNG and binary PGM via tw_decode_gray; JPEG is not decoded -- SURVEY row f-1).  uv_thread / uv_mutex / uv_cond become std::thread /
 // std::mutex / std::condition_variable; the uv_async hop to the V8 main loop does not exist: Manager::work calls the
 // observer directly.  There is no CPU operator: every consumer needs a CUDA device (id % device count).
 #pragma once
@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <mutex>
 #include <queue>
 #include <string>
@@ -61,23 +62,17 @@ struct Plane { // cv::Mat, CV_32FC1
     float at(int y, int x) const { return data[(size_t)y * cols + x]; }
 };
 
-// cv::imread(path, IMREAD_GRAYSCALE) for binary PGM (P5, maxval 255); anything else -> empty image
+// cv::imread(path, IMREAD_GRAYSCALE): PNG and binary PGM through tw_decode_gray; anything else -> empty image
 inline Image imread_gray(const std::string &path)
 {
     Image img;
     std::ifstream f(path.c_str(), std::ios::binary);
     if (!f) return img;
-    std::string magic;
-    f >> magic;
-    if (magic != "P5") return img;
-    int w = 0, h = 0, maxv = 0;
-    auto skip = [&]() { while (f >> std::ws && f.peek() == '#') { std::string line; std::getline(f, line); } };
-    skip(); f >> w; skip(); f >> h; skip(); f >> maxv;
-    f.get();
-    if (!f || w <= 0 || h <= 0 || maxv != 255) return img;
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    int w = 0, h = 0;
+    if (bytes.empty() || tw_decode_gray(bytes.data(), bytes.size(), NULL, 0, &w, &h) != TW_OK) return img;
     img.data.resize((size_t)w * h);
-    f.read(reinterpret_cast<char *>(img.data.data()), (std::streamsize)img.data.size());
-    if (!f) { img.data.clear(); return img; }
+    if (tw_decode_gray(bytes.data(), bytes.size(), img.data.data(), img.data.size(), &w, &h) != TW_OK) { img.data.clear(); return img; }
     img.rows = h; img.cols = w;
     return img;
 }
