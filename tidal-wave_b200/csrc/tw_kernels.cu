@@ -388,9 +388,9 @@ cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, con
         return cudaGetLastError();
     }
     if (int_scale == 2 && a.ksize == 3) return launch_pyr<2, 3, 64, 15>(s, fa, a.nimg);
-    if (int_scale == 4 && a.ksize == 9) return launch_pyr<4, 9, 32, 16>(s, fa, a.nimg);
-    if (int_scale == 8 && a.ksize == 19) return launch_pyr<8, 19, 16, 10>(s, fa, a.nimg);
-    if (int_scale == 16 && a.ksize == 39) return launch_pyr<16, 39, 8, 4>(s, fa, a.nimg);
+    if (int_scale == 4 && a.ksize == 9) return launch_pyr<4, 9, 32, 6>(s, fa, a.nimg);
+    if (int_scale == 8 && a.ksize == 19) return launch_pyr<8, 19, 16, 6>(s, fa, a.nimg);
+    if (int_scale == 16 && a.ksize == 39) return launch_pyr<16, 39, 8, 2>(s, fa, a.nimg);
     return cudaErrorNotSupported;
 }
 
