@@ -46,7 +46,6 @@ struct Plan {
     uint8_t *src = nullptr; // [B][2][H][spitch]
     int spitch = 0;
     double *V = nullptr; // box only
-    float *last_M = nullptr;
 };
 
 } // namespace
@@ -497,7 +496,6 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             }
             if (!ia.last) std::swap(Min, Mout);
         }
-        pl.last_M = Min;
     }
     if (span > 0) {
         Scale &f = pl.scales.back();

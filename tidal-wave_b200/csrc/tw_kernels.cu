@@ -1072,18 +1072,22 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
         for (int r = 0; r < NIN; r++)
             in[r] = __ldg(reinterpret_cast<const float2 *>(row_ptr(base, rsb, (unsigned)clampi(ybase + r, 0, h - 1))));
     }
+    // taps outer, outputs inner: 8 independent accumulator chains are interleaved explicitly
+    float2 v[G2_RV];
 #pragma unroll
-    for (int o = 0; o < G2_RV; o++) {
-        float2 v = tw_mul2(in[o + MR], make_float2(t.k[0], t.k[0]));
+    for (int o = 0; o < G2_RV; o++) v[o] = tw_mul2(in[o + MR], make_float2(t.k[0], t.k[0]));
 #pragma unroll
-        for (int i = 1; i <= MR; i++) {
+    for (int i = 1; i <= MR; i++) {
+        const float2 kk = make_float2(t.k[i], t.k[i]);
+#pragma unroll
+        for (int o = 0; o < G2_RV; o++) {
             const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
-            const float2 kk = make_float2(t.k[i], t.k[i]);
-            if (FMA) v = tw_fma2(sum, kk, v);
-            else v = tw_fma2(tw_mul2(sum, kk), one2, v); // = v + round(sum * k): see tw_fma2 note
+            if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
+            else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]); // = v + round(sum * k): see tw_fma2 note
         }
-        dst[o * dstride] = v;
     }
+#pragma unroll
+    for (int o = 0; o < G2_RV; o++) dst[o * dstride] = v[o];
 }
 
 // 5 items per thread: (G11,G12) and (G22,h1) float2 planes at (column j, row groups g and g+2), then the h2 plane at
@@ -1206,19 +1210,22 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
                     const float4 u = src[q];
                     v[2 * q] = make_float2(u.x, u.y); v[2 * q + 1] = make_float2(u.z, u.w);
                 }
+                float2 sacc[4];
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const int ctr = p + 16 - LO;
-                    float2 sacc = tw_mul2(v[ctr], make_float2(t.k[0], t.k[0]));
+                for (int p = 0; p < 4; p++) sacc[p] = tw_mul2(v[p + 16 - LO], make_float2(t.k[0], t.k[0]));
 #pragma unroll
-                    for (int i = 1; i <= MR; i++) {
+                for (int i = 1; i <= MR; i++) {
+                    const float2 kk = make_float2(t.k[i], t.k[i]);
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const int ctr = p + 16 - LO;
                         const float2 sum = tw_add2(v[ctr - i], v[ctr + i]);
-                        const float2 kk = make_float2(t.k[i], t.k[i]);
-                        if (FMA) sacc = tw_fma2(kk, sum, sacc);
-                        else sacc = tw_fma2(tw_mul2(kk, sum), one2, sacc);
+                        if (FMA) sacc[p] = tw_fma2(kk, sum, sacc[p]);
+                        else sacc[p] = tw_fma2(tw_mul2(kk, sum), one2, sacc[p]);
                     }
-                    if (pr) r23[p] = sacc; else r01[p] = sacc;
                 }
+#pragma unroll
+                for (int p = 0; p < 4; p++) { if (pr) r23[p] = sacc[p]; else r01[p] = sacc[p]; }
             }
             {
                 const float4 *src = reinterpret_cast<const float4 *>(P4 + lane * G2_P4 + cbase + LO);
