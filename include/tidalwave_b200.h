@@ -27,7 +27,7 @@ enum tw_error_code {
     TW_BAD_IMAGE_FORMAT = 2,
     TW_DONT_MATCH_SIZE = 3,
     TW_CUDA_ERROR = 4,   /* reason carries cudaGetErrorString */
-    TW_UNSUPPORTED = 5   /* documented gap (e.g. +-5 px resize path before row f-2 lands) */
+    TW_UNSUPPORTED = 5   /* reserved for documented gaps (currently unused) */
 };
 
 /* Response.status, src/consumer.cpp:77,86 */
