@@ -1090,6 +1090,60 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
     for (int o = 0; o < G2_RV; o++) dst[o * dstride] = v[o];
 }
 
+// Column walker: one thread owns one column of one channel pair for ALL rows of the tile.  The 8+2*MR-row register
+// window slides down by 8 rows per group; the 8 new rows of the next group are requested BEFORE the current group's
+// 8 x (1 + 3*MR) packed operations, so only the first window of a tile exposes load latency, and a tile column is
+// read 32+2*MR times instead of 4 x (8+2*MR).
+template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
+__device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
+                                              int dstride, int ybase, int h, const WinTaps &t)
+{
+    constexpr int NIN = G2_RV + 2 * MR, NG = GK_TH / G2_RV;
+    const float2 one2 = make_float2(t.one, t.one);
+    const unsigned rsb = (unsigned)rstride * 8u;
+    const char *base = reinterpret_cast<const char *>(src);
+    if (INTERIOR) base = row_ptr(base, rsb, (unsigned)ybase);
+    auto ld = [&](int r) -> float2 {
+        if (INTERIOR) {
+            if (CPITCH) return __ldg(reinterpret_cast<const float2 *>(base) + (size_t)r * rstride);
+            return __ldg(reinterpret_cast<const float2 *>(row_ptr(base, rsb, (unsigned)r)));
+        }
+        return __ldg(reinterpret_cast<const float2 *>(row_ptr(base, rsb, (unsigned)clampi(ybase + r, 0, h - 1))));
+    };
+    float2 win[NIN];
+#pragma unroll
+    for (int r = 0; r < NIN; r++) win[r] = ld(r);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        float2 nxt[G2_RV];
+        if (g + 1 < NG) {
+#pragma unroll
+            for (int r = 0; r < G2_RV; r++) nxt[r] = ld(NIN + G2_RV * g + r);
+        }
+        float2 v[G2_RV];
+#pragma unroll
+        for (int o = 0; o < G2_RV; o++) v[o] = tw_mul2(win[o + MR], make_float2(t.k[0], t.k[0]));
+#pragma unroll
+        for (int i = 1; i <= MR; i++) {
+            const float2 kk = make_float2(t.k[i], t.k[i]);
+#pragma unroll
+            for (int o = 0; o < G2_RV; o++) {
+                const float2 sum = tw_add2(win[o + MR + i], win[o + MR - i]);
+                if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
+                else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < G2_RV; o++) dst[(G2_RV * g + o) * dstride] = v[o];
+        if (g + 1 < NG) {
+#pragma unroll
+            for (int r = 0; r < NIN - G2_RV; r++) win[r] = win[r + G2_RV];
+#pragma unroll
+            for (int r = 0; r < G2_RV; r++) win[NIN - G2_RV + r] = nxt[r];
+        }
+    }
+}
+
 // 5 items per thread: (G11,G12) and (G22,h1) float2 planes at (column j, row groups g and g+2), then the h2 plane at
 // (column pair jj, row group g) -- every item is "38 8-byte loads, 8 packed outputs".  Columns are replicated by
 // clamping the address; the h2 column pair is clamped as a pair (x0 and w are even multiples of the tile / pitch
@@ -1101,13 +1155,13 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
     float2 *P01 = reinterpret_cast<float2 *>(sm);
     float2 *P23 = P01 + GK_TH * G2_P2;
     float2 *P4 = P23 + GK_TH * G2_P2; // float2 view of the plain float plane (pitch 132 floats = 66 float2)
-#pragma unroll 1
-    for (int it = 0; it < 4; it++) {
-        const int pair = it >> 1, j = tid & 127, g = (tid >> 7) + 2 * (it & 1);
+    {
+        // 256 threads = 128 columns x 2 channel pairs, each walking the 32 rows of the tile
+        const int pair = tid >> 7, j = tid & 127;
         const int gx = clampi(x0 - 16 + j, 0, w - 1);
         const float2 *src = reinterpret_cast<const float2 *>(Min + pair * 2 * pitch) + gx;
-        float2 *dst = (pair ? P23 : P01) + g * G2_RV * G2_P2 + j;
-        gauss_v_item2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 + g * G2_RV - MR, h, t);
+        float2 *dst = (pair ? P23 : P01) + j;
+        gauss_v_walk2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 - MR, h, t);
     }
     {
         const int jj = tid & 63, g = tid >> 6;
