@@ -235,3 +235,46 @@ def test_pool_stop_drops_pending(tw, golden):
     assert rep["request"] == 50 and rep["data"] + sum(g is None for g in got) == 50
     assert pool.request(s1, s1) < 0
     pool.close()
+
+
+def test_deterministic_and_context_independent(tw):
+    """Same input -> bit-identical output, across repeats, across contexts and across batch slots (no atomics on the data path,
+    no uninitialised reads)."""
+    a, b = tw.synth.make_pair("S", 640, 360, 77, defect=True)
+    o1 = tw.OpticalFlow(0, 640, 360, 3)
+    o2 = tw.OpticalFlow(0, 640, 360, 1)
+    rc, fx1, fy1, _ = o1.calculateInternal(a, b)
+    rc, fx2, fy2, _ = o1.calculateInternal(a, b)
+    rc, fx3, fy3, _ = o2.calculateInternal(a, b)
+    assert np.array_equal(fx1, fx2) and np.array_equal(fy1, fy2) and np.array_equal(fx1, fx3) and np.array_equal(fy1, fy3)
+    c, d = tw.synth.make_pair("T", 640, 360, 78)
+    rb = o1.calculate_batch([(c, d), (a, b), (c, d)])
+    fxb, fyb = o1.batch_flow(1, 640, 360)
+    assert np.array_equal(fxb, fx1) and np.array_equal(fyb, fy1)
+    assert rb[1] == {**o2.calculate(a, b), "time": rb[1]["time"]}
+    o1.close(); o2.close()
+
+
+def test_concurrent_contexts(tw):
+    """Two consumers on the same GPU (two contexts / streams) running at once give the single-context answers."""
+    import threading
+    pairs = [tw.synth.make_pair("S", 480, 270, 90 + i, defect=(i % 2 == 0)) for i in range(6)]
+    ref = tw.OpticalFlow(0, 480, 270, 1)
+    want = [ref.calculate(a, b) for a, b in pairs]
+    ref.close()
+    out = [None, None]
+
+    def work(k):
+        o = tw.OpticalFlow(0, 480, 270, 2)
+        res = []
+        for _ in range(3):
+            res = [o.calculate(a, b) for a, b in pairs]
+        out[k] = res
+        o.close()
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in range(2):
+        for w_, g in zip(want, out[k]):
+            assert w_["status"] == g["status"] and w_["vector"] == g["vector"]
