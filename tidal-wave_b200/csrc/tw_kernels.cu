@@ -1387,8 +1387,21 @@ __global__ void __launch_bounds__(128) box_vsum_kernel(const float *__restrict__
     const int h = d.h, pitch = d.pitch * 5;
     double vs = (double)(M[0] * (float)(m + 2));
     for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * pitch];
-#pragma unroll 4
-    for (int y = 0; y < h; y++) {
+    // 16 rows per step: the 32 loads and 16 float differences are independent (issued together), only the double
+    // accumulation is sequential; each thread writes whole 32-byte sectors of its VT row.
+    int y = 0;
+    for (; y + 16 <= h; y += 16) {
+        float diff[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            diff[k] = __ldg(M + (size_t)min(y + k + m, h - 1) * pitch) - __ldg(M + (size_t)max(y + k - m - 1, 0) * pitch);
+        double o[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { vs = vs + (double)diff[k]; o[k] = vs; }
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) *reinterpret_cast<double2 *>(v + y + k) = make_double2(o[k], o[k + 1]);
+    }
+    for (; y < h; y++) {
         float diff = __ldg(M + (size_t)min(y + m, h - 1) * pitch) - __ldg(M + (size_t)max(y - m - 1, 0) * pitch);
         vs = vs + (double)diff;
         v[y] = vs;
@@ -1424,20 +1437,30 @@ __global__ void __launch_bounds__(128) box_hscan_kernel(const double *__restrict
     float *fxp = flow + (size_t)b * 2 * d.plane, *fyp = fxp + d.plane;
     for (int xc = 0; xc < w; xc += 32) {
         const int n = min(32, w - xc);
-#pragma unroll 4
-        for (int i = 0; i < n; i++) {
-            const int x = xc + i;
-            const size_t oa = (size_t)min(x + m, w - 1) * pitchT, ob = (size_t)max(x - m - 1, 0) * pitchT;
-            double bb[5];
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            // the differences V[x+m] - V[x-m-1] of 4 steps are independent: load and subtract them first
+            double dv[4][5];
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                g[c] = g[c] + (V[c * planeT + oa] - V[c * planeT + ob]);
-                bb[c] = g[c] * scale;
+            for (int u = 0; u < 4; u++) {
+                const int x = min(xc + i0 + u, w - 1);
+                const size_t oa = (size_t)min(x + m, w - 1) * pitchT, ob = (size_t)max(x - m - 1, 0) * pitchT;
+#pragma unroll
+                for (int c = 0; c < 5; c++) dv[u][c] = V[c * planeT + oa] - V[c * planeT + ob];
             }
-            float fx, fy;
-            solve2x2d(bb[0], bb[1], bb[2], bb[3], bb[4], fx, fy);
-            tile[warp][0][lane][i] = fx;
-            tile[warp][1][lane][i] = fy;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + u >= n) break;
+                double bb[5];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    g[c] = g[c] + dv[u][c];
+                    bb[c] = g[c] * scale;
+                }
+                float fx, fy;
+                solve2x2d(bb[0], bb[1], bb[2], bb[3], bb[4], fx, fy);
+                tile[warp][0][lane][i0 + u] = fx;
+                tile[warp][1][lane][i0 + u] = fy;
+            }
         }
         __syncwarp();
         for (int r = 0; r < 32 && y0 + r < h; r++) {
