@@ -120,7 +120,7 @@ def test_kernel_variants_agree(tw, oracle):
     for the same arithmetic: all bit-identical to the default path."""
     a, b = tw.synth.make_pair("S", 480, 300, 33, defect=True)
     ref = oracle.farneback(a, b, FlowParam())
-    for opt in (None, "gauss_scalar", "level_generic", "tight_pitch"):
+    for opt in (None, "gauss_scalar", "level_generic", "level_unfused", "tight_pitch"):
         o = tw.OpticalFlow(0, 480, 300, 1)
         if opt:
             o.set_option(opt, 1)

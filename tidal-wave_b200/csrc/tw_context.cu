@@ -46,6 +46,7 @@ struct Plan {
     uint8_t *src = nullptr; // [B][2][H][spitch]
     int spitch = 0;
     double *V = nullptr; // box only
+    bool fused_levels = false;
 };
 
 } // namespace
@@ -57,7 +58,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
-    int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_tight_pitch = 0;
+    int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -358,21 +359,27 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
     }
     // work buffers: shared across scales (sized for the finest) unless keep_levels
     const Scale &fine = pl.scales.back();
-    float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr;
+    float *R = nullptr, *M0 = nullptr, *M1 = nullptr;
     if (!ctx->keep_levels) {
-        if (!dev_alloc(ctx, &I, (size_t)B * 2 * fine.d.plane) || !dev_alloc(ctx, &R, (size_t)B * 10 * fine.d.plane) ||
+        if (!dev_alloc(ctx, &R, (size_t)B * 10 * fine.d.plane) ||
             !dev_alloc(ctx, &M0, (size_t)B * 5 * fine.d.plane) || !dev_alloc(ctx, &M1, (size_t)B * 5 * fine.d.plane))
             return false;
     }
     for (Scale &s : pl.scales) {
+        // level images are small (2 planes) and, on the fused path, all written up front: one buffer per scale
+        if (!dev_alloc(ctx, &s.I, (size_t)B * 2 * s.d.plane)) return false;
         if (ctx->keep_levels) {
-            if (!dev_alloc(ctx, &s.I, (size_t)B * 2 * s.d.plane) || !dev_alloc(ctx, &s.R, (size_t)B * 10 * s.d.plane) ||
+            if (!dev_alloc(ctx, &s.R, (size_t)B * 10 * s.d.plane) ||
                 !dev_alloc(ctx, &s.M0, (size_t)B * 5 * s.d.plane) || !dev_alloc(ctx, &s.M1, (size_t)B * 5 * s.d.plane))
                 return false;
         } else {
-            s.I = I; s.R = R; s.M0 = M0; s.M1 = M1;
+            s.R = R; s.M0 = M0; s.M1 = M1;
         }
     }
+    // the default pyramid (full resolution + exact 2x / 4x / 8x with 3 / 9 / 19-tap pre-blurs) takes the fused level kernel
+    pl.fused_levels = pl.scales.size() == 4 && pl.scales[3].identity && pl.scales[3].ksize == 3 && pl.scales[2].int_scale == 2 &&
+                      pl.scales[2].ksize == 3 && pl.scales[1].int_scale == 4 && pl.scales[1].ksize == 9 && pl.scales[0].int_scale == 8 &&
+                      pl.scales[0].ksize == 19 && (9 + 2 < std::min(W, H));
     if (p.flags == 0 && !dev_alloc(ctx, &pl.V, (size_t)B * 5 * (size_t)(fine.d.w + 32) * (size_t)(fine.d.h + 32))) return false;
     pl.valid = true;
     return true;
@@ -444,6 +451,15 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         cudaError_t e = cudaMemsetAsync(ctx->d_counts, 0, sizeof(int) * n, ctx->stream);
         if (e != cudaSuccess) { set_err(ctx, "memset counts", e); return false; }
     }
+    const bool fused_levels = pl.fused_levels && !ctx->opt_level_generic && !ctx->opt_level_unfused;
+    if (fused_levels) {
+        float *dst[4]; LevelDims dd[4];
+        double bytes = 0;
+        for (int i = 0; i < 4; i++) { dst[i] = pl.scales[i].I; dd[i] = pl.scales[i].d; bytes += n * (2 * P0 + 8.0 * dd[i].w * dd[i].h); }
+        LAUNCH(F_LEVEL, bytes, launch_level_fused(ctx->stream, pl.src, W, H, pl.spitch, dst, dd, pl.scales[0].host_taps.data(),
+                                                   pl.scales[1].host_taps.data(), pl.scales[2].host_taps.data(),
+                                                   pl.scales[3].host_taps.data(), 2 * n));
+    }
     for (size_t si = 0; si < ns; si++) {
         Scale &s = pl.scales[si];
         const double Pl = (double)s.d.w * s.d.h;
@@ -454,7 +470,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         la.identity = s.identity;
         la.small = (s.ksize / 2 + 2 >= std::min(W, H));
         // I planes of a batch are laid out [B][2]: the u8 source is [B][2] too, so image index = blockIdx.z.
-        {
+        if (!fused_levels) {
             LaunchScope ls_(ctx, F_LEVEL, n * (2 * P0 + 8 * Pl));
             cudaError_t e_ = ctx->opt_level_generic ? cudaErrorNotSupported : launch_level_image_fast(ctx->stream, la, s.host_taps.data(), s.int_scale);
             if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
@@ -899,6 +915,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;

@@ -375,6 +375,166 @@ static cudaError_t launch_pyr(cudaStream_t s, const LevelFastArgs &fa, int nimg)
     return cudaGetLastError();
 }
 
+// (c) all four level images of the reference's default pyramid (pyrScale 0.5, pyrLevels 3 on a frame whose sides are
+// multiples of 8: full resolution + S = 2, 4, 8) from ONE staged source tile: the u8 -> float staging, the dominant
+// cost of (a)/(b), is paid once instead of four times and three launches disappear.  One CTA = 16 x 6 outputs of the
+// coarsest level = 128 x 48 source pixels (+ halo).  Arithmetic per level is exactly that of (a) / (b).
+constexpr int LF_TW3 = 16, LF_TH3 = 6, LF_SH = 60, LF_SWP = 148, LF_RPP = 65;
+constexpr size_t LF_SMEM = sizeof(float) * ((size_t)LF_SH * LF_SWP + (size_t)LF_SH * LF_RPP * 2);
+
+struct LevelFusedArgs {
+    const uint8_t *src; // [nimg][H][spitch]
+    int W, H, spitch;
+    float *dst[4];      // [nimg][h][pitch] for S = 8, 4, 2, 1 (coarse -> fine, the plan's scale order)
+    LevelDims d[4];
+    float k8[19], k4[9], k2[3], k1[3];
+};
+
+// row pass of scale S over the whole staged tile (lane = tile row), two adjacent source columns per output column
+template <int S, int K, int TWO, int BASE>
+__device__ __forceinline__ void lf_row_pass(const float *__restrict__ tile, float2 *__restrict__ rp, const float *__restrict__ k, int lane, int warp)
+{
+    constexpr int C = K / 2;
+    constexpr int OFFL = S / 2 - 1 - C + 8 - BASE;              // tile column of tap 0 of output column 0, minus BASE
+    constexpr int CPI = S >= 4 ? 1 : 4 / S;
+    constexpr int NLD = (OFFL + K + 1 + S * (CPI - 1) + 3) / 4;
+    constexpr int RPP = TWO + 1;
+    static_assert(OFFL >= 0 && BASE % 4 == 0, "alignment");
+    for (int rb = 0; rb < LF_SH; rb += 32) {
+        const int r = rb + lane;
+        if (r >= LF_SH) continue;
+        for (int dp = warp; dp < TWO / CPI; dp += 8) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(tile + r * LF_SWP + BASE + S * CPI * dp);
+            float v[NLD * 4];
+#pragma unroll
+            for (int q = 0; q < NLD; q++) {
+                const float4 u = p4[q];
+                v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+            }
+#pragma unroll
+            for (int u = 0; u < CPI; u++) {
+                const int b = OFFL + S * u;
+                float o0, o1;
+                if (K == 3) {
+                    o0 = fmaf(v[b + 1], k[1], (v[b] + v[b + 2]) * k[0]);
+                    o1 = fmaf(v[b + 2], k[1], (v[b + 1] + v[b + 3]) * k[0]);
+                } else {
+                    o0 = v[b] * k[0];
+                    o1 = v[b + 1] * k[0];
+#pragma unroll
+                    for (int j = 1; j < K; j++) {
+                        o0 = fmaf(v[b + j], k[j], o0);
+                        o1 = fmaf(v[b + 1 + j], k[j], o1);
+                    }
+                }
+                rp[r * RPP + CPI * dp + u] = make_float2(o0, o1);
+            }
+        }
+    }
+}
+
+template <int S, int K, int TWO, int THO>
+__device__ __forceinline__ void lf_col_pass(const float2 *__restrict__ rp, const float *__restrict__ k, float *__restrict__ dst, const LevelDims &d,
+                                            int d0, int e0, int tid)
+{
+    constexpr int C = K / 2, RPP = TWO + 1;
+    constexpr int ROFF = S / 2 - 1 - C + 6; // tile row of tap 0 of output row 0
+    for (int i = tid; i < TWO * THO; i += 256) {
+        const int el = i / TWO, dl = i - el * TWO;
+        const int dd = d0 + dl, e = e0 + el;
+        if (dd >= d.w || e >= d.h) continue;
+        const float2 *q = rp + (ROFF + S * el + C) * RPP + dl;
+        float2 ra, rb2;
+        if (K == 3) {
+            const float2 u = q[-RPP], c0 = q[0], c1 = q[RPP], dn = q[2 * RPP];
+            ra = make_float2(fmaf(u.x + c1.x, k[0], c0.x * k[1]), fmaf(u.y + c1.y, k[0], c0.y * k[1]));
+            rb2 = make_float2(fmaf(c0.x + dn.x, k[0], c1.x * k[1]), fmaf(c0.y + dn.y, k[0], c1.y * k[1]));
+        } else {
+            const float2 c0 = q[0], c1 = q[RPP];
+            ra = make_float2(c0.x * k[C], c0.y * k[C]);
+            rb2 = make_float2(c1.x * k[C], c1.y * k[C]);
+#pragma unroll
+            for (int j = 1; j <= C; j++) {
+                const float2 am = q[-j * RPP], ap = q[j * RPP], bm = q[(1 - j) * RPP], bp = q[(1 + j) * RPP];
+                ra.x = fmaf(am.x + ap.x, k[C + j], ra.x); ra.y = fmaf(am.y + ap.y, k[C + j], ra.y);
+                rb2.x = fmaf(bm.x + bp.x, k[C + j], rb2.x); rb2.y = fmaf(bm.y + bp.y, k[C + j], rb2.y);
+            }
+        }
+        const float fx = 0.5f, gx = 1.f - fx, fy = 0.5f, gy = 1.f - fy;
+        const float r0 = ra.x * gx + ra.y * fx;
+        const float r1 = rb2.x * gx + rb2.y * fx;
+        dst[(size_t)e * d.pitch + dd] = r0 * gy + r1 * fy;
+    }
+}
+
+__global__ void __launch_bounds__(256) level_fused_kernel(LevelFusedArgs a)
+{
+    extern __shared__ __align__(16) float lf_smem[];
+    float *tile = lf_smem;                                              // [60][148]
+    float2 *rp = reinterpret_cast<float2 *>(lf_smem + LF_SH * LF_SWP);  // [60][<= 65]
+    const int d0 = blockIdx.x * LF_TW3, e0 = blockIdx.y * LF_TH3;       // coarsest-level tile origin
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *src = a.src + (size_t)blockIdx.z * a.H * a.spitch;
+    stage_tile_u8<LF_SH, LF_SWP>(src, a.spitch, a.W, a.H, 8 * d0 - 8, 8 * e0 - 6, tile, warp, lane);
+    __syncthreads();
+
+    // full resolution (3-tap blur, no resize): thread = column x 24 rows, rolling window; tile col = x - 8*d0 + 8, row = y - 8*e0 + 6
+    {
+        const int col = tid & 127, g = tid >> 7;
+        const int x = 8 * d0 + col;
+        if (x < a.d[3].w) {
+            const float k0 = a.k1[0], k1 = a.k1[1];
+            const float *p = tile + (g * 24 + 5) * LF_SWP + col + 7; // left neighbour of x in the row above the first output row
+            float *dst = a.dst[3] + (size_t)blockIdx.z * a.d[3].plane + x;
+            float h0 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+            p += LF_SWP;
+            float h1 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+#pragma unroll
+            for (int i = 0; i < 24; i++) {
+                p += LF_SWP;
+                const float h2 = fmaf(p[1], k1, (p[0] + p[2]) * k0);
+                const int y = 8 * e0 + g * 24 + i;
+                if (y < a.d[3].h) dst[(size_t)y * a.d[3].pitch] = fmaf(h0 + h2, k0, h1 * k1);
+                h0 = h1; h1 = h2;
+            }
+        }
+    }
+    // S = 2 (K = 3), 64 x 24 outputs
+    lf_row_pass<2, 3, 64, 4>(tile, rp, a.k2, lane, warp);
+    __syncthreads();
+    lf_col_pass<2, 3, 64, 24>(rp, a.k2, a.dst[2] + (size_t)blockIdx.z * a.d[2].plane, a.d[2], 4 * d0, 4 * e0, tid);
+    __syncthreads();
+    // S = 4 (K = 9), 32 x 12 outputs
+    lf_row_pass<4, 9, 32, 4>(tile, rp, a.k4, lane, warp);
+    __syncthreads();
+    lf_col_pass<4, 9, 32, 12>(rp, a.k4, a.dst[1] + (size_t)blockIdx.z * a.d[1].plane, a.d[1], 2 * d0, 2 * e0, tid);
+    __syncthreads();
+    // S = 8 (K = 19), 16 x 6 outputs
+    lf_row_pass<8, 19, 16, 0>(tile, rp, a.k8, lane, warp);
+    __syncthreads();
+    lf_col_pass<8, 19, 16, 6>(rp, a.k8, a.dst[0] + (size_t)blockIdx.z * a.d[0].plane, a.d[0], d0, e0, tid);
+}
+
+cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H, int spitch, float *const dst[4], const LevelDims d[4],
+                               const float *k8, const float *k4, const float *k2, const float *k1, int nimg)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(level_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    LevelFusedArgs a{};
+    a.src = src; a.W = W; a.H = H; a.spitch = spitch;
+    for (int i = 0; i < 4; i++) { a.dst[i] = dst[i]; a.d[i] = d[i]; }
+    for (int i = 0; i < 19; i++) a.k8[i] = k8[i];
+    for (int i = 0; i < 9; i++) a.k4[i] = k4[i];
+    for (int i = 0; i < 3; i++) { a.k2[i] = k2[i]; a.k1[i] = k1[i]; }
+    dim3 grid((d[0].w + LF_TW3 - 1) / LF_TW3, (d[0].h + LF_TH3 - 1) / LF_TH3, nimg);
+    level_fused_kernel<<<grid, 256, LF_SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+
 // Returns cudaErrorNotSupported when no fast path applies (the caller then uses the generic kernel).
 cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, const float *host_taps, int int_scale)
 {

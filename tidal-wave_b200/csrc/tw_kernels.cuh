@@ -51,6 +51,9 @@ cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a);
 // Fast paths (full-resolution level; exact integer down-scales 2/4/8/16).  int_scale = S if W == w*S, H == h*S and the
 // resize tables are exactly (S*d + S/2 - 1, 0.5), else 0.  Returns cudaErrorNotSupported if none applies.
 cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, const float *host_taps, int int_scale);
+// All four level images of the default pyramid (S = 8, 4, 2, 1 with 19/9/3/3-tap pre-blurs) from one staged source tile.
+cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H, int spitch, float *const dst[4], const LevelDims d[4],
+                               const float *k8, const float *k4, const float *k2, const float *k1, int nimg);
 size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity);
 
 // K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
