@@ -888,8 +888,15 @@ __global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
     // kernel (measured: two pixels per thread at 78 registers was 15 % slower).
     if (PITCH) { a.d.pitch = PITCH; a.cd.pitch = PITCH; } // compile-time row pitch: the 4 bilinear neighbours become load immediates
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= a.d.w || y >= a.d.h) return;
     const int b = blockIdx.z;
+    // The R1 gather can only be addressed after the table and coarse-flow loads (two dependent latencies): start the
+    // DRAM -> L2 transfer of this warp's R0 / R1 row segments now (lanes 0..9 = image x channel).
+    if (a.M && threadIdx.x < 10 && y < a.d.h) {
+        const float *Rb = a.R + (size_t)b * 10 * a.d.plane + (size_t)(threadIdx.x / 5) * 5 * a.d.plane;
+        const int xs = min((int)blockIdx.x * 32, a.d.w - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + ((size_t)y * 5 + threadIdx.x % 5) * a.d.pitch + xs));
+    }
+    if (x >= a.d.w || y >= a.d.h) return;
     float dx, dy;
     upsample_flow_px(a, b, x, y, dx, dy);
     if (a.flow_out) {
