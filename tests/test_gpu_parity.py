@@ -278,3 +278,17 @@ def test_concurrent_contexts(tw):
     for k in range(2):
         for w_, g in zip(want, out[k]):
             assert w_["status"] == g["status"] and w_["vector"] == g["vector"]
+
+
+def test_pool_all_devices(tw, golden):
+    """One process, one consumer per visible GPU (the reference's consumer i <-> GPU i, src/consumer.cpp:18-24): kernel
+    attributes are per device, so every device must be able to launch every kernel.  (On a 1-GPU box this is devices=[0].)"""
+    n = tw.load().tw_device_count()
+    a, b = golden["imgs"]["s2_expected"], golden["imgs"]["s2_revision2"]
+    pool = tw.Pool(list(range(n)) * 2, batch=2, max_w=180, max_h=117)
+    ids = [pool.request(a, b) for _ in range(8 * n)]
+    out = [pool.wait(i) for i in ids]
+    rep = pool.report()
+    pool.stop(); pool.close()
+    assert rep == {"request": 8 * n, "data": 8 * n, "error": 0}
+    assert all(r["status"] == "SUSPICIOUS" and len(r["vector"]) == 24 for r in out)

@@ -10,6 +10,16 @@
 
 namespace tw {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was configured per device, not
+// per process (an in-process multi-GPU pool launches the same kernel on every device).
+constexpr int kMaxDevices = 64;
+static int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // base + stride * row as ONE instruction (IMAD.WIDE.U32).  nvcc otherwise strength-reduces the unrolled row
@@ -178,7 +188,8 @@ size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a)
 {
     size_t smem = level_image_smem_bytes(a.smem_w, a.smem_h, a.tile_w, a.ksize, a.identity);
-    static size_t configured[2] = {0, 0};
+    static size_t configured_dev[kMaxDevices][2] = {};
+    size_t *configured = configured_dev[current_device()];
     if (smem > 48 * 1024 && smem > configured[a.identity ? 1 : 0]) {
         cudaError_t e = a.identity ? cudaFuncSetAttribute(level_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                    : cudaFuncSetAttribute(level_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -364,7 +375,8 @@ template <int S, int K, int TWO, int THO>
 static cudaError_t launch_pyr(cudaStream_t s, const LevelFastArgs &fa, int nimg)
 {
     using G = PyrGeom<S, K, TWO, THO>;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(level_pyr_kernel<S, K, TWO, THO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         if (e != cudaSuccess) return e;
@@ -518,7 +530,8 @@ __global__ void __launch_bounds__(256) level_fused_kernel(LevelFusedArgs a)
 cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H, int spitch, float *const dst[4], const LevelDims d[4],
                                const float *k8, const float *k4, const float *k2, const float *k1, int nimg)
 {
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(level_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM);
         if (e != cudaSuccess) return e;
@@ -1486,7 +1499,8 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
 template <int MR, bool FMA, int PITCH>
 static cudaError_t launch_gauss_fast2p(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
         if (e != cudaSuccess) return e;
@@ -1508,7 +1522,8 @@ static cudaError_t launch_gauss_fast2(cudaStream_t s, const IterArgs &a, const W
 template <int MR, bool FMA>
 static cudaError_t launch_gauss_fast(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gauss_iter_kernel<MR, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GK_SMEM);
         if (e != cudaSuccess) return e;
