@@ -377,9 +377,13 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         }
     }
     // the default pyramid (full resolution + exact 2x / 4x / 8x with 3 / 9 / 19-tap pre-blurs) takes the fused level kernel
-    pl.fused_levels = pl.scales.size() == 4 && pl.scales[3].identity && pl.scales[3].ksize == 3 && pl.scales[2].int_scale == 2 &&
-                      pl.scales[2].ksize == 3 && pl.scales[1].int_scale == 4 && pl.scales[1].ksize == 9 && pl.scales[0].int_scale == 8 &&
-                      pl.scales[0].ksize == 19 && (9 + 2 < std::min(W, H));
+    // (the FINEST four scales; deeper pyramids keep their coarser scales on the per-level kernels)
+    {
+        const size_t nsc = pl.scales.size();
+        pl.fused_levels = nsc >= 4 && pl.scales[nsc - 1].identity && pl.scales[nsc - 1].ksize == 3 && pl.scales[nsc - 2].int_scale == 2 &&
+                          pl.scales[nsc - 2].ksize == 3 && pl.scales[nsc - 3].int_scale == 4 && pl.scales[nsc - 3].ksize == 9 &&
+                          pl.scales[nsc - 4].int_scale == 8 && pl.scales[nsc - 4].ksize == 19 && (9 + 2 < std::min(W, H));
+    }
     if (p.flags == 0 && !dev_alloc(ctx, &pl.V, (size_t)B * 5 * (size_t)(fine.d.w + 32) * (size_t)(fine.d.h + 32))) return false;
     pl.valid = true;
     return true;
@@ -452,13 +456,17 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         if (e != cudaSuccess) { set_err(ctx, "memset counts", e); return false; }
     }
     const bool fused_levels = pl.fused_levels && !ctx->opt_level_generic && !ctx->opt_level_unfused;
+    const size_t fbase = ns >= 4 ? ns - 4 : 0; // first scale produced by the fused kernel
     if (fused_levels) {
         float *dst[4]; LevelDims dd[4];
         double bytes = 0;
-        for (int i = 0; i < 4; i++) { dst[i] = pl.scales[i].I; dd[i] = pl.scales[i].d; bytes += n * (2 * P0 + 8.0 * dd[i].w * dd[i].h); }
-        LAUNCH(F_LEVEL, bytes, launch_level_fused(ctx->stream, pl.src, W, H, pl.spitch, dst, dd, pl.scales[0].host_taps.data(),
-                                                   pl.scales[1].host_taps.data(), pl.scales[2].host_taps.data(),
-                                                   pl.scales[3].host_taps.data(), 2 * n));
+        for (int i = 0; i < 4; i++) {
+            dst[i] = pl.scales[fbase + i].I; dd[i] = pl.scales[fbase + i].d;
+            bytes += n * (2 * P0 + 8.0 * dd[i].w * dd[i].h);
+        }
+        LAUNCH(F_LEVEL, bytes, launch_level_fused(ctx->stream, pl.src, W, H, pl.spitch, dst, dd, pl.scales[fbase].host_taps.data(),
+                                                   pl.scales[fbase + 1].host_taps.data(), pl.scales[fbase + 2].host_taps.data(),
+                                                   pl.scales[fbase + 3].host_taps.data(), 2 * n));
     }
     for (size_t si = 0; si < ns; si++) {
         Scale &s = pl.scales[si];
@@ -470,7 +478,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         la.identity = s.identity;
         la.small = (s.ksize / 2 + 2 >= std::min(W, H));
         // I planes of a batch are laid out [B][2]: the u8 source is [B][2] too, so image index = blockIdx.z.
-        if (!fused_levels) {
+        if (!fused_levels || si < fbase) {
             LaunchScope ls_(ctx, F_LEVEL, n * (2 * P0 + 8 * Pl));
             cudaError_t e_ = ctx->opt_level_generic ? cudaErrorNotSupported : launch_level_image_fast(ctx->stream, la, s.host_taps.data(), s.int_scale);
             if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
