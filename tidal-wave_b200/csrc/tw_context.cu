@@ -311,8 +311,11 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         resize_coeffs(H, s.d.h, yi, yf);
         s.identity = (s.d.w == W && s.d.h == H);
         const int c = s.ksize / 2;
-        // choose an output tile whose float source tile + row-pass buffer leave room for >= 2 CTAs per SM
+        // choose an output tile whose float source tile + row-pass buffer leave room for >= 2 CTAs per SM (<= 64 KB); with
+        // very long pre-blur kernels (79 taps at 1/32 scale) such a tile would hold only a handful of outputs behind a huge
+        // halo, so fall back to the largest tile that fits one CTA per SM (<= 160 KB)
         int tw_ = s.identity ? 128 : 64, th_ = 16;
+        int big_tw = 0, big_th = 0, big_sw = 0, big_sh = 0;
         for (;;) {
             int sw = 0, sh = 0;
             for (int d0 = 0; d0 < s.d.w; d0 += tw_) {
@@ -325,9 +328,11 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
             }
             sw = (sw + 3 + 4) & ~3; // the staging loop writes whole 4-column words
             size_t bytes = level_image_smem_bytes(sw, sh, tw_, s.ksize, s.identity);
+            if (!big_tw && bytes <= 160 * 1024) { big_tw = tw_; big_th = th_; big_sw = sw; big_sh = sh; }
             if (bytes <= 64 * 1024 || (tw_ == 1 && th_ == 1)) {
                 if (bytes > 200 * 1024) { ctx->err = "pre-blur kernel too large for shared memory"; return false; }
                 s.smem_w = sw; s.smem_h = sh;
+                if (tw_ * th_ < 32 && big_tw * big_th > tw_ * th_) { tw_ = big_tw; th_ = big_th; s.smem_w = big_sw; s.smem_h = big_sh; }
                 break;
             }
             if (tw_ >= th_ * 2 && tw_ > 1) tw_ /= 2; else if (th_ > 1) th_ /= 2; else tw_ /= 2;

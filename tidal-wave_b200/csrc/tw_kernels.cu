@@ -118,36 +118,35 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
     }
     __syncthreads();
 
-    // row pass, only at the source columns the resize reads
+    // row pass, only at the source columns the resize reads; (row, slot) items are spread over all 256 threads (tiles
+    // behind a long pre-blur kernel are only a few columns wide)
     const int ncol = IDENT ? tw_ : tw_ * 2;
-    for (int slot = lane; slot < ncol; slot += 32) {
+    for (int i = threadIdx.x; i < SH * ncol; i += 256) {
+        const int r = i / ncol, slot = i - r * ncol;
         int xl; // local column of tap 0
         if (IDENT) xl = d0 + slot - c - xs_lo;
         else xl = min(a.xi[d0 + (slot >> 1)] + (slot & 1), W - 1) - c - xs_lo;
+        const float *p = tile + r * SWp + xl;
+        float o;
         if (K == 3) {
-            const float k0 = ktab[0], k1 = ktab[1];
-            for (int r = warp; r < SH; r += 8) {
-                const float *p = tile + r * SWp + xl;
-                rp[r * NC + slot] = fmaf(p[1], k1, (p[0] + p[2]) * k0);
-            }
+            o = fmaf(p[1], ktab[1], (p[0] + p[2]) * ktab[0]);
         } else {
-            for (int r = warp; r < SH; r += 8) {
-                const float *p = tile + r * SWp + xl;
-                float o = p[0] * ktab[0];
-                for (int j = 1; j < K; j++) o = fmaf(p[j], ktab[j], o);
-                rp[r * NC + slot] = o;
-            }
+            o = p[0] * ktab[0];
+#pragma unroll 4
+            for (int j = 1; j < K; j++) o = fmaf(p[j], ktab[j], o);
         }
+        rp[r * NC + slot] = o;
     }
     __syncthreads();
 
     // column pass at the source rows the resize reads, then the bilinear blend (A.2b)
     float *dst = a.dst + (size_t)blockIdx.z * a.d.plane;
-    for (int ty = warp; ty < th_; ty += 8) {
+    for (int i = threadIdx.x; i < th_ * tw_; i += 256) {
+        const int ty = i / tw_, tx = i - ty * tw_;
         const int e = e0 + ty;
         const int y0 = a.yi[e], y1 = min(y0 + 1, H - 1);
         const float fy = IDENT ? 0.f : a.yf[e];
-        for (int tx = lane; tx < tw_; tx += 32) {
+        {
             const int d = d0 + tx;
             float res[2][2];
 #pragma unroll
