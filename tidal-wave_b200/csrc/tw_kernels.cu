@@ -391,7 +391,8 @@ static cudaError_t launch_pyr(cudaStream_t s, const LevelFastArgs &fa, int nimg)
 // cost of (a)/(b), is paid once instead of four times and three launches disappear.  One CTA = 16 x 6 outputs of the
 // coarsest level = 128 x 48 source pixels (+ halo).  Arithmetic per level is exactly that of (a) / (b).
 constexpr int LF_TW3 = 16, LF_TH3 = 6, LF_SH = 60, LF_SWP = 148, LF_RPP = 65;
-constexpr size_t LF_SMEM = sizeof(float) * ((size_t)LF_SH * LF_SWP + (size_t)LF_SH * LF_RPP * 2);
+constexpr int LF_RAWP = 176; // bytes per staged raw row: 148 source columns + up to 8 of 16-byte alignment slack, multiple of 16
+constexpr size_t LF_SMEM = sizeof(float) * ((size_t)LF_SH * LF_SWP + (size_t)LF_SH * LF_RPP * 2) + 16; // + mbarrier
 
 struct LevelFusedArgs {
     const uint8_t *src; // [nimg][H][spitch]
@@ -486,7 +487,46 @@ __global__ void __launch_bounds__(256) level_fused_kernel(LevelFusedArgs a)
     const int d0 = blockIdx.x * LF_TW3, e0 = blockIdx.y * LF_TH3;       // coarsest-level tile origin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *src = a.src + (size_t)blockIdx.z * a.H * a.spitch;
-    stage_tile_u8<LF_SH, LF_SWP>(src, a.spitch, a.W, a.H, 8 * d0 - 8, 8 * e0 - 6, tile, warp, lane);
+    const int xs_lo = 8 * d0 - 8, ys_lo = 8 * e0 - 6, xs16 = xs_lo & ~15;
+    // Interior tiles (no REFLECT_101 needed) are staged by the TMA engine: 60 bulk row copies global -> shared
+    // (cp.async.bulk, completion on an mbarrier), then one pass converts the raw bytes to the float tile.  The raw
+    // buffer aliases the row-pass buffer, which is not live yet.  Border tiles take the per-thread reflecting loads.
+    const bool interior = xs_lo >= 0 && xs_lo + LF_SWP <= a.W && xs16 + LF_RAWP <= a.spitch && ys_lo >= 0 && ys_lo + LF_SH <= a.H;
+    if (interior) {
+        unsigned char *raw = reinterpret_cast<unsigned char *>(rp);
+        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(lf_smem + LF_SH * LF_SWP + LF_SH * LF_RPP * 2);
+        const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(LF_SH * LF_RAWP) : "memory");
+            const uint8_t *g = src + (size_t)ys_lo * a.spitch + xs16;
+            const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw);
+            for (int r = 0; r < LF_SH; r++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(raw_s + r * LF_RAWP),
+                             "l"(g + (size_t)r * a.spitch), "r"(LF_RAWP), "r"(mbar_s)
+                             : "memory");
+        }
+        __syncthreads(); // the mbarrier is initialised before anybody polls it
+        unsigned done = 0;
+        for (int spin = 0; !done; spin++) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar_s) : "memory");
+            if (spin > (1 << 24)) __trap(); // never hang the GPU on a lost completion
+        }
+        const int off = xs_lo - xs16; // 0 or 8
+        for (int i = tid; i < LF_SH * (LF_SWP / 4); i += 256) {
+            const int r = i / (LF_SWP / 4), q4 = i - r * (LF_SWP / 4);
+            const unsigned w0 = *reinterpret_cast<const unsigned *>(raw + r * LF_RAWP + off + 4 * q4);
+            float4 f;
+            f.x = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7650)) - 8388608.0f;
+            f.y = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7651)) - 8388608.0f;
+            f.z = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7652)) - 8388608.0f;
+            f.w = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7653)) - 8388608.0f;
+            *reinterpret_cast<float4 *>(tile + r * LF_SWP + 4 * q4) = f;
+        }
+    } else {
+        stage_tile_u8<LF_SH, LF_SWP>(src, a.spitch, a.W, a.H, xs_lo, ys_lo, tile, warp, lane);
+    }
     __syncthreads();
 
     // full resolution (3-tap blur, no resize): thread = column x 24 rows, rolling window; tile col = x - 8*d0 + 8, row = y - 8*e0 + 6
