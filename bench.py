@@ -246,13 +246,13 @@ def main():
     # DRAM traffic per launch of that family from the committed ncu --set full capture (same command line, same batch)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1k_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1m_traffic.json")))
         if tj.get("batch") == B and top in tj:
             traffic = tj[top]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1k_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None, "peak_source": peak_src, "avg_launch_ms": tv["ms"] / tv["launches"],
+                "traffic": traffic, "traffic_source": "profiles/r1m_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None, "peak_source": peak_src, "avg_launch_ms": tv["ms"] / tv["launches"],
                 "alg_bytes_per_launch": tv["alg_bytes"] / tv["launches"], "share_of_step": tv["ms"] / kernel_ms_total,
                 "pipeline": {"alg_bytes_per_pair": alg_total / (B * args.steps), "achieved": alg_total / (elapsed_ms * 1e-3) / 1e9,
                              "frac": alg_total / (elapsed_ms * 1e-3) / 1e9 / peak},
@@ -308,7 +308,7 @@ def main():
         fma_ms = dist.reduce_max(float(ms.value))
         of.set_option("gauss_fma", 0)
         variants = {"gauss_fma": {"value": tw.dist.whole_job_throughput(B * nv, world, fma_ms * 1e-3), "unit": UNIT,
-                                  "note": "tw_set_option(gauss_fma): <= 1.4e-3 px from the oracle (profiles/r1k_parity_fullsize.jsonl), "
+                                  "note": "tw_set_option(gauss_fma): <= 1.4e-3 px from the oracle (profiles/r1m_parity_fullsize.jsonl), "
                                           "not bit-exact; the headline value uses the bit-faithful arithmetic"}}
 
     cpu = None
