@@ -125,10 +125,24 @@ int tw_sync(tw_ctx *ctx);
 /* Copies the dense flow planes of pair `pair` of the last run back (either pointer may be NULL). */
 int tw_batch_flow(tw_ctx *ctx, int pair, float *flowx, float *flowy);
 const char *tw_last_error(tw_ctx *ctx);
-/* Opt-in arithmetic relaxations (default 0 = bit-faithful to the oracle's operation order):
- *   "gauss_fma" = 1: fused multiply-add in the Gaussian window tap sums (<= 2e-4 px on the
- *                    default options; never applied to the box window). */
+/* Per-context options.
+ *   "arithmetic" = 0: every kernel keeps the oracle's operation order: results bit-identical to
+ *                     oracle/farneback_ref.c on every configuration.
+ *                = 1 (default; TW_ARITHMETIC=faithful in the environment or tw_set_default_arithmetic(0) flips it):
+ *                     relaxed arithmetic where it was validated -- Gaussian window (flags 256) with winSize >= 30 and
+ *                     polyN 7, i.e. the reference's default option family: fmaf in the window tap sums and a mixed
+ *                     double / float horizontal pass in the polynomial expansion.  Measured against the faithful oracle
+ *                     and cv2: <= 2.6e-4 px at 1920x1080, 2.1e-3 px max / 1.2e-4 px RMS on the reference's fixture,
+ *                     identical status and vector sets (bar: 1e-2 px max, 1e-3 px RMS; tools/relax_study.py).  Every
+ *                     other option set (box window, smaller windows, polyN != 7) runs the faithful kernels.
+ *   "graph"      = 1 (default): repeated runs of one (size, batch, options) replay a captured CUDA graph.
+ *   "gauss_fma"  = 1: fmaf in the Gaussian window tap sums only (part of "arithmetic" = 1).
+ *   "gauss_scalar", "level_generic", "level_unfused", "tight_pitch": alternative code paths kept for the parity tests. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);
+/* Process-wide default of "arithmetic" for contexts created afterwards (the dispatcher's consumers included). */
+int tw_set_default_arithmetic(int relaxed);
+/* 1 if `param` would run the relaxed kernels on this context, 0 if the faithful ones, <0 on bad arguments. */
+int tw_arithmetic_in_effect(tw_ctx *ctx, const tw_flow_param *param);
 
 /* Pinned (page-locked) host memory for image buffers: H2D copies from it are true async DMA. */
 void *tw_host_alloc(size_t bytes);

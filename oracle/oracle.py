@@ -71,6 +71,11 @@ class RefOracle:
         L.twref_farneback_dump.restype = C.c_int
         L.twref_sample.restype = C.c_int
 
+    def set_relax(self, bits: int) -> None:
+        """Relaxed-arithmetic variants of the restatement (farneback_ref.c, twref_set_relax): 0 = faithful App. A;
+        17 = what the product's "arithmetic" = 1 runs (fmaf window taps + mixed double/float poly-exp pass)."""
+        self.lib.twref_set_relax(int(bits))
+
     @staticmethod
     def _cparam(p: FlowParam) -> _CParam:
         return _CParam(p.pyrScale, p.pyrLevels, p.winSize, p.pyrIterations, p.polyN, p.polySigma, p.flags)

@@ -14,6 +14,15 @@ pytestmark = pytest.mark.gpu
 TOL_MAX, TOL_RMS = 1e-2, 1e-3
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _faithful_arithmetic(tw):
+    """This module pins the FAITHFUL arithmetic (bit-identical to the oracle); the library default -- relaxed where
+    validated -- is covered by tests/test_gpu_relaxed.py."""
+    tw.set_default_arithmetic(False)
+    yield
+    tw.set_default_arithmetic(True)
+
+
 @pytest.fixture(scope="module")
 def of(tw):
     o = tw.OpticalFlow(0, 1920, 1080, 4)

@@ -9,5 +9,5 @@ operator interface), synth.py (seeded synthetic screenshot pairs).
 """
 from . import dist, synth, tidalwave  # noqa: F401
 from .tidalwave import TidalWave, create, run  # noqa: F401
-from .api import (LIB_PATH, imread_gray, OpticalFlow, OpticalFlowParameter, Pool, declared_symbols, load, tw_flow_param,  # noqa: F401
+from .api import (LIB_PATH, imread_gray, OpticalFlow, OpticalFlowParameter, Pool, declared_symbols, load, set_default_arithmetic, tw_flow_param,  # noqa: F401
                   tw_result, tw_vector)

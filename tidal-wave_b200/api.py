@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     L.tw_host_free.argtypes = [C.c_void_p]
     L.tw_l2_flush.argtypes = [C.c_void_p]
     L.tw_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.tw_set_default_arithmetic.argtypes = [C.c_int]
+    L.tw_arithmetic_in_effect.argtypes = [C.c_void_p, C.POINTER(tw_flow_param)]
     L.tw_timer_start.argtypes = [C.c_void_p]
     L.tw_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tw_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -114,6 +116,12 @@ def load() -> C.CDLL:
     L.tw_pool_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def set_default_arithmetic(relaxed: bool) -> None:
+    """Process-wide default of the "arithmetic" option for contexts created afterwards (pool consumers included):
+    False = faithful (SURVEY App. A operation order), True = relaxed where validated (include/tidalwave_b200.h)."""
+    load().tw_set_default_arithmetic(1 if relaxed else 0)
 
 
 def declared_symbols() -> list[str]:
@@ -182,6 +190,11 @@ class OpticalFlow:
 
     def last_error(self) -> str:
         return self.lib.tw_last_error(self.ctx).decode()
+
+    def arithmetic_in_effect(self, param: "OpticalFlowParameter" = None) -> str:
+        """'relaxed' or 'faithful': which kernels `param` runs on this context."""
+        p = (param or OpticalFlowParameter()).c()
+        return "relaxed" if self.lib.tw_arithmetic_in_effect(self.ctx, C.byref(p)) == 1 else "faithful"
 
     def calculateInternal(self, expectImg, targetImg, param: OpticalFlowParameter = OpticalFlowParameter()):
         """-> (code, flowx, flowy, seconds); src/opticalflow.cpp:78-119."""

@@ -4,6 +4,7 @@
 #include "../../include/tidalwave_b200.h"
 #include "tw_kernels.cuh"
 
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -59,6 +60,20 @@ struct tw_ctx {
     Plan plan;
     int keep_levels = 0;
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
+    int opt_arith = 1;  // 0 = faithful (App. A operation order), 1 = relaxed where validated (relaxed_in_effect)
+    int opt_graph = 1;  // replay the launch sequence of a batch from a captured CUDA graph
+    // CUDA graph of the launch sequence (enqueue) for one (plan, n, threshold, span, options) key
+    struct GraphKey {
+        unsigned long long plan_gen = 0; int n = 0; double thr = 0; int span = 0; int opts = 0; const void *vectors = nullptr;
+        bool operator==(const GraphKey &o) const
+        {
+            return plan_gen == o.plan_gen && n == o.n && thr == o.thr && span == o.span && opts == o.opts && vectors == o.vectors;
+        }
+    };
+    GraphKey graph_key, seen_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0;
+    unsigned long long plan_gen = 0;
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -100,8 +115,17 @@ bool set_err(tw_ctx *c, const char *what, cudaError_t e)
         if (e_ != cudaSuccess) { set_err(ctx, #call, e_); return false; } \
     } while (0)
 
+void drop_graph(tw_ctx *ctx)
+{
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    ctx->graph_key = tw_ctx::GraphKey();
+    ctx->seen_key = tw_ctx::GraphKey();
+}
+
 void free_plan(tw_ctx *ctx)
 {
+    drop_graph(ctx);
+    ctx->plan_gen++;
     for (void *p : ctx->plan.allocs) cudaFree(p);
     ctx->plan = Plan();
 }
@@ -223,6 +247,7 @@ void poly_tables(int n, double sigma, PolyTables &t)
     invert6(G, inv);
     t.n = n;
     t.ig11 = inv[1][1]; t.ig03 = inv[0][3]; t.ig33 = inv[3][3]; t.ig55 = inv[5][5];
+    t.fig11 = (float)t.ig11; t.fig55 = (float)t.ig55;
     for (int x = 0; x <= n; x++) {
         t.g[x] = g[x]; t.xg[x] = xg[x]; t.xxg[x] = xxg[x];
         t.gd[x] = (double)g[x]; t.xxgd[x] = (double)xxg[x];
@@ -446,11 +471,22 @@ bool ensure_results(tw_ctx *ctx, int cap)
     return true;
 }
 
+// Relaxed arithmetic (fmaf in the Gaussian window taps, mixed double / float horizontal pass of the polynomial
+// expansion) is used only for the option family it was validated on against the faithful oracle and cv2
+// (tools/relax_study.py, tests/test_gpu_parity.py): Gaussian window of the reference's default size or larger and
+// polyN = 7.  Smaller windows and the box window are measured to be chaotic under ANY reordering and
+// always run the faithful kernels.
+bool relaxed_in_effect(const tw_ctx *ctx, const tw_flow_param &p)
+{
+    return ctx->opt_arith == 1 && (p.flags & 256) && p.winSize >= 30 && p.polyN == 7;
+}
+
 // The launch sequence for n pairs already resident in plan.src.  SURVEY App. A.1 / A.7.
 bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
 {
     Plan &pl = ctx->plan;
     const tw_flow_param &p = pl.p;
+    const bool relaxed = relaxed_in_effect(ctx, p);
     const int W = pl.W, H = pl.H;
     const double P0 = (double)W * H;
     const size_t ns = pl.scales.size();
@@ -489,7 +525,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
             if (e_ != cudaSuccess) { set_err(ctx, "launch_level_image", e_); return false; }
         }
-        LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly));
+        LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly, relaxed ? 1 : 0));
 
         FirstUpdateArgs fa{};
         if (si > 0) {
@@ -509,7 +545,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
             ia.last = (it == p.pyrIterations - 1);
             if (fused_count && ia.last && si + 1 == ns) { ia.span = span; ia.thr2 = threshold * threshold; ia.counts = ctx->d_counts; }
-            ia.fma = ctx->opt_gauss_fma;
+            ia.fma = (ctx->opt_gauss_fma || relaxed) ? 1 : 0;
             ia.scalar = ctx->opt_gauss_scalar;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
             if (p.flags & 256) {
@@ -538,12 +574,84 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
     return true;
 }
 
+// enqueue() directly, or -- from the second run with an unchanged (plan, n, threshold, span, options) key on -- as ONE
+// cudaGraphLaunch of the captured sequence (the step is ~22 short launches; at the coarse scales the kernels are
+// shorter than their launch gaps).  The first run of a key is always eager: it configures the per-device kernel
+// attributes and sizes the result buffers outside any capture.  Profiling (per-family events) runs eagerly.
+bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
+{
+    if (!ctx->opt_graph || ctx->profiling) return enqueue(ctx, n, threshold, span);
+    tw_ctx::GraphKey key;
+    key.plan_gen = ctx->plan_gen; key.n = n; key.thr = threshold; key.span = span;
+    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4;
+    key.vectors = ctx->d_vectors;
+    if (ctx->graph_exec && key == ctx->graph_key) {
+        cudaError_t e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+        if (e != cudaSuccess) { set_err(ctx, "cudaGraphLaunch", e); return false; }
+        ctx->launches += ctx->graph_launches;
+        return true;
+    }
+    if (!(key == ctx->seen_key)) { // first run of this key: eager
+        if (!enqueue(ctx, n, threshold, span)) return false;
+        ctx->seen_key = key;
+        ctx->seen_key.vectors = ctx->d_vectors; // enqueue may have (re)allocated the result buffer
+        return true;
+    }
+    // second run: capture, instantiate, launch
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    const long long before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { // capture unavailable: stay eager
+        cudaGetLastError();
+        ctx->opt_graph = 0;
+        return enqueue(ctx, n, threshold, span);
+    }
+    const bool ok = enqueue(ctx, n, threshold, span);
+    e = cudaStreamEndCapture(ctx->stream, &graph);
+    const long long captured = ctx->launches - before;
+    ctx->launches = before;
+    if (!ok || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->opt_graph = 0; // never retry on this context; the eager path is the same launch sequence
+        if (!ok) return false;
+        return enqueue(ctx, n, threshold, span);
+    }
+    e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->graph_exec = nullptr;
+        ctx->opt_graph = 0;
+        return enqueue(ctx, n, threshold, span);
+    }
+    ctx->graph_key = key;
+    ctx->graph_launches = captured;
+    e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "cudaGraphLaunch", e); return false; }
+    ctx->launches += captured;
+    return true;
+}
+
 void fill_error(tw_result *r, int code, const char *msg)
 {
     memset(r, 0, sizeof *r);
     r->code = code;
     r->status = TW_STATUS_ERROR;
     snprintf(r->reason, sizeof r->reason, "%s", msg);
+}
+
+std::atomic<int> g_default_arith{-1}; // -1: not decided yet (TW_ARITHMETIC or 1)
+
+int default_arith()
+{
+    int v = g_default_arith.load();
+    if (v >= 0) return v;
+    const char *env = getenv("TW_ARITHMETIC");
+    v = (env && (!strcmp(env, "faithful") || !strcmp(env, "0"))) ? 0 : 1;
+    g_default_arith.store(v);
+    return v;
 }
 
 } // namespace
@@ -585,6 +693,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     }
     tw_ctx *ctx = new tw_ctx();
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
+    ctx->opt_arith = default_arith();
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
     cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
     if ((e = cudaMalloc(&ctx->d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
@@ -727,7 +836,7 @@ int tw_batch_run(tw_ctx *ctx, int n, int w, int h, const tw_flow_param *param, d
         if (!ok) return TW_CUDA_ERROR;
     }
     cudaEventRecord(ctx->ev_r0, ctx->stream);
-    if (!enqueue(ctx, n, threshold, span)) return TW_CUDA_ERROR;
+    if (!run_sequence(ctx, n, threshold, span)) return TW_CUDA_ERROR;
     cudaEventRecord(ctx->ev_r1, ctx->stream);
     ctx->last_n = n; ctx->last_w = w; ctx->last_h = h; ctx->ran = true;
     return TW_OK;
@@ -925,6 +1034,8 @@ long long tw_launch_count(tw_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int tw_set_option(tw_ctx *ctx, const char *name, int value)
 {
     if (!ctx || !name) return TW_BAD_PARAMETER;
+    if (!strcmp(name, "arithmetic")) { ctx->opt_arith = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "graph")) { ctx->opt_graph = value ? 1 : 0; if (!value) drop_graph(ctx); return TW_OK; }
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
@@ -932,6 +1043,18 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;
+}
+
+int tw_set_default_arithmetic(int relaxed)
+{
+    g_default_arith.store(relaxed ? 1 : 0);
+    return TW_OK;
+}
+
+int tw_arithmetic_in_effect(tw_ctx *ctx, const tw_flow_param *param)
+{
+    if (!ctx || !param) return -1;
+    return relaxed_in_effect(ctx, *param) ? 1 : 0;
 }
 
 int tw_debug_keep_levels(tw_ctx *ctx, int on)

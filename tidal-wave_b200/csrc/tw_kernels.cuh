@@ -18,6 +18,7 @@ struct PolyTables {
     float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
     double gd[kMaxPolyN + 1], xxgd[kMaxPolyN + 1]; // (double)g[k], (double)xxg[k]: no conversions in the tap loop
     double ig11, ig03, ig33, ig55;
+    float fig11, fig55; // (float)ig11, (float)ig55: relaxed-arithmetic kernel
     int n;
 };
 
@@ -57,7 +58,8 @@ cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H,
 size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity);
 
 // K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
-cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t);
+// relaxed = 1: the mixed double/float horizontal pass (polyN 5 / 7 only; otherwise the faithful kernels run).
+cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, int relaxed);
 
 // K3: (coarse flow -> bilinear upsample * 1/pyrScale | zero) -> first update-matrices, App. A.1 + A.4.
 struct FirstUpdateArgs {

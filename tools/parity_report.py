@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Parity report on a B200: CUDA path vs the C oracle (and cv2 when importable) on BASELINE.json's configs at full size,
-faithful and with the opt-in gauss_fma relaxation.  Writes one JSON line per case.  usage: tools/parity_report.py [--quick]"""
+with the faithful arithmetic and with the library default (relaxed where validated); the relaxed result is also compared
+bit for bit with the oracle's restatement of the same relaxation (twref_set_relax(17)).  Writes one JSON line per case.  usage: tools/parity_report.py [--quick]"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,10 +31,10 @@ for name, (kind, W, H, seed, defect), kw in cases:
     except Exception:
         cvf = None
     row = dict(case=name, oracle_s=round(t_or, 2))
-    for mode in ("faithful", "gauss_fma"):
-        if mode == "gauss_fma" and kw.get("flags", 256) == 0:
+    for mode in ("faithful", "relaxed"):
+        of.set_option("arithmetic", int(mode == "relaxed"))
+        if mode == "relaxed" and of.arithmetic_in_effect(tw.OpticalFlowParameter(**kw)) != "relaxed":
             continue
-        of.set_option("gauss_fma", int(mode == "gauss_fma"))
         rc, fx, fy, sec = of.calculateInternal(a, b, tw.OpticalFlowParameter(**kw))
         assert rc == 0, of.last_error()
         fl = np.stack([fx, fy], -1)
@@ -42,10 +43,15 @@ for name, (kind, W, H, seed, defect), kw in cases:
                   bit_equal=float((fl == ref).mean()), gpu_ms=round(sec * 1e3, 3),
                   status_same=sample_numpy(fl)[0] == O.sample(ref)[0],
                   vectors_same=[(v[0], v[1]) for v in sample_numpy(fl)[1]] == [(v[0], v[1]) for v in O.sample(ref)[1]])
+        if mode == "relaxed":
+            O.set_relax(17)
+            rel = O.farneback(a, b, FlowParam(**kw))
+            O.set_relax(0)
+            st["bit_equal_relaxed_oracle"] = float((fl == rel).mean())
         if cvf is not None:
             dc = np.abs(fl - cvf)
             st["vs_cv2_max"] = float(dc.max()); st["vs_cv2_rms"] = float(np.sqrt((dc ** 2).mean()))
             st["cv2_status_same"] = sample_numpy(fl)[0] == sample_numpy(cvf)[0]
         row[mode] = st
-    of.set_option("gauss_fma", 0)
+    of.set_option("arithmetic", 1)
     print(json.dumps(row), flush=True)
