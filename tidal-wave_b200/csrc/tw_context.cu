@@ -694,6 +694,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     tw_ctx *ctx = new tw_ctx();
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
     ctx->opt_arith = default_arith();
+    if (const char *g = getenv("TW_GRAPH")) ctx->opt_graph = atoi(g) ? 1 : 0; // TW_GRAPH=0: eager launches (profilers)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
     cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
     if ((e = cudaMalloc(&ctx->d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
