@@ -350,8 +350,8 @@ def main():
                                        "(-0.37,+0.61) px, every 8th with a defect), default options (threshold 5, span 10, pyrLevels 3, "
                                        "winSize 30, pyrIterations 3, polyN 7, polySigma 1.5, flags 256)" % B,
                            "batch": B,
-                           "arithmetic": ("relaxed (library default for this option family): fmaf in the Gaussian window taps + mixed "
-                                          "double/float horizontal poly-exp pass; measured <= 2.6e-4 px from the faithful oracle at "
+                           "arithmetic": ("relaxed (library default for this option family): direct-form fmaf Gaussian window taps + mixed "
+                                          "double/float horizontal poly-exp pass; measured <= 1.5e-4 px from the faithful oracle at "
                                           "1920x1080 (bar 1e-2), status and vectors identical; tests/test_gpu_relaxed.py")
                            if arithmetic == "relaxed" else "faithful: the oracle's operation order, bit-identical results",
                            "launch": "one CUDA graph replay per step (%d kernel nodes)" % (launches // max(args.steps, 1)),

@@ -2,7 +2,7 @@
 CUDA-graph replay of the launch sequence.  Everything goes through the C ABI.
 
 The relaxed kernels are checked twice:
-  * bit for bit against the SAME relaxation restated in the oracle (oracle/farneback_ref.c, twref_set_relax(17)) --
+  * bit for bit against the SAME relaxation restated in the oracle (oracle/farneback_ref.c, twref_set_relax(144)) --
     so the kernels compute exactly the documented arithmetic, and
   * within the north-star tolerance (BASELINE.json: 1e-2 px max-abs, 1e-3 px RMS, identical classification) against the
     FAITHFUL oracle and the committed cv2 flows.
@@ -17,7 +17,7 @@ from oracle.oracle import FlowParam, sample_numpy
 pytestmark = pytest.mark.gpu
 
 TOL_MAX, TOL_RMS = 1e-2, 1e-3
-RELAX_BITS = 17  # fmaf window taps (1) + mixed double/float horizontal poly-exp pass (16)
+RELAX_BITS = 144  # direct-form fmaf window taps (128) + mixed double/float horizontal poly-exp pass (16)
 # The reference's scenario2 fixture iterated 5 times per scale is chaotic for EVERY implementation: cv2 4.13.0 itself moves by
 # 0.24 px between cv2.setUseOptimized(True) and (False) on it (0.014 px at 4 iterations, 7e-4 px at the default 3), so no
 # build of the reference's library pins it to 1e-2 px.  There the relaxed kernels are held to bit-equality with the restated
@@ -105,6 +105,26 @@ def test_arithmetic_option_switches(tw, oracle):
         for _ in range(3):  # eager, capture, replay
             rc, fx, fy, _ = o.calculateInternal(a, b)
             assert rc == 0 and np.array_equal(fx, want[..., 0]) and np.array_equal(fy, want[..., 1]), mode
+    o.close()
+
+
+def test_update_fma_opt_in_is_relax_bit_6(tw, oracle):
+    """The studied (rejected as default) update-matrices relaxation stays reachable and is exactly oracle bit 6 on top of
+    the default relaxation; a defect pair with a motion boundary drives both the shared-row and the per-pixel epilogue paths."""
+    a, b = tw.synth.make_pair("S", 480, 300, 33, defect=True)
+    oracle.set_relax(RELAX_BITS | 64)
+    rel = oracle.farneback(a, b, FlowParam())
+    oracle.set_relax(0)
+    o = tw.OpticalFlow(0, 480, 300, 1)
+    o.set_option("update_fma", 1)
+    rc, fx, fy, _ = o.calculateInternal(a, b)
+    assert rc == 0 and np.array_equal(fx, rel[..., 0]) and np.array_equal(fy, rel[..., 1])
+    o.set_option("update_fma", 0)
+    oracle.set_relax(RELAX_BITS)
+    rel = oracle.farneback(a, b, FlowParam())
+    oracle.set_relax(0)
+    rc, fx, fy, _ = o.calculateInternal(a, b)
+    assert rc == 0 and np.array_equal(fx, rel[..., 0]) and np.array_equal(fy, rel[..., 1])
     o.close()
 
 

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtidalwave_b200.so")
+LIB_PATH = os.environ.get("TW_LIB") or os.path.join(_HERE, "libtidalwave_b200.so")  # TW_LIB: development builds (tools/timeline.py)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tidalwave_b200.h")
 
 OK, BAD_PARAMETER, BAD_IMAGE_FORMAT, DONT_MATCH_SIZE, CUDA_ERROR, UNSUPPORTED = range(6)

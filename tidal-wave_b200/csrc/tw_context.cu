@@ -59,6 +59,7 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
+    int opt_update_fma = 0; // studied opt-in (oracle relax bit 6), never part of "arithmetic" = 1
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
     int opt_arith = 1;  // 0 = faithful (App. A operation order), 1 = relaxed where validated (relaxed_in_effect)
     int opt_graph = 1;  // replay the launch sequence of a batch from a captured CUDA graph
@@ -534,6 +535,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         }
         fa.inv_scale = (float)(1. / p.pyrScale);
         fa.R = s.R; fa.d = s.d; fa.batch = n;
+        fa.ufma = (relaxed && ctx->opt_update_fma) ? 1 : 0;
         fa.M = p.pyrIterations > 0 ? s.M0 : nullptr;
         fa.flow_out = p.pyrIterations > 0 ? nullptr : s.flow;
         double cbytes = si > 0 ? 8.0 * pl.scales[si - 1].d.w * pl.scales[si - 1].d.h : 0.0;
@@ -545,7 +547,8 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             ia.Min = Min; ia.Mout = Mout; ia.R = s.R; ia.flow = s.flow; ia.d = s.d; ia.batch = n;
             ia.last = (it == p.pyrIterations - 1);
             if (fused_count && ia.last && si + 1 == ns) { ia.span = span; ia.thr2 = threshold * threshold; ia.counts = ctx->d_counts; }
-            ia.fma = (ctx->opt_gauss_fma || relaxed) ? 1 : 0;
+            ia.fma = relaxed ? 2 : (ctx->opt_gauss_fma ? 1 : 0);
+            ia.ufma = (ia.fma == 2 && ctx->opt_update_fma) ? 1 : 0;
             ia.scalar = ctx->opt_gauss_scalar;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
             if (p.flags & 256) {
@@ -556,6 +559,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
                 if (!ia.last) {
                     FirstUpdateArgs ua{};
                     ua.flow_in = s.flow; ua.R = s.R; ua.M = Mout; ua.d = s.d; ua.batch = n; ua.inv_scale = 1.f;
+                    ua.ufma = 0;
                     LAUNCH(F_BUPD, 0.0, launch_first_update(ctx->stream, ua));
                 }
             }
@@ -583,7 +587,7 @@ bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
     if (!ctx->opt_graph || ctx->profiling) return enqueue(ctx, n, threshold, span);
     tw_ctx::GraphKey key;
     key.plan_gen = ctx->plan_gen; key.n = n; key.thr = threshold; key.span = span;
-    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4;
+    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5;
     key.vectors = ctx->d_vectors;
     if (ctx->graph_exec && key == ctx->graph_key) {
         cudaError_t e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
@@ -1038,6 +1042,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "arithmetic")) { ctx->opt_arith = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "graph")) { ctx->opt_graph = value ? 1 : 0; if (!value) drop_graph(ctx); return TW_OK; }
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "update_fma")) { ctx->opt_update_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }

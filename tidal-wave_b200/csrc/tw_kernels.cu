@@ -998,48 +998,75 @@ __device__ __forceinline__ void upd_load(const float *__restrict__ R0, const flo
     }
 }
 
-__device__ __forceinline__ void upd_compute(const UpdLoad &L, int w, int h, int x, int y, float dx, float dy, float m[5])
+// UF = validated relaxation (oracle relax bit 6): fmaf chains in the bilinear blend, the flow terms and the outer
+// products (same association order as App. A.4); UF = false keeps the oracle's mul / add sequence (-fmad=false TU).
+// pt / pb = R1 at rows y1 / y1+1, columns (x1, x1+1); q = R0 at (x, y).
+template <bool UF, bool BORDER = true>
+__device__ __forceinline__ void upd_core(const float q[5], const float pt[5][2], const float pb[5][2], bool inside, float fx, float fy,
+                                         int w, int h, int x, int y, float dx, float dy, float m[5])
 {
-    float r2, r3, r4, r5, r6;
-    if (L.inside) {
-        const float fx = L.fx, fy = L.fy;
+    float r[5];
+    if (inside) {
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        r2 = a00 * L.p[0][0] + a01 * L.p[0][1] + a10 * L.p[0][2] + a11 * L.p[0][3];
-        r3 = a00 * L.p[1][0] + a01 * L.p[1][1] + a10 * L.p[1][2] + a11 * L.p[1][3];
-        r4 = a00 * L.p[2][0] + a01 * L.p[2][1] + a10 * L.p[2][2] + a11 * L.p[2][3];
-        r5 = a00 * L.p[3][0] + a01 * L.p[3][1] + a10 * L.p[3][2] + a11 * L.p[3][3];
-        r6 = a00 * L.p[4][0] + a01 * L.p[4][1] + a10 * L.p[4][2] + a11 * L.p[4][3];
-        r4 = (L.q[2] + r4) * 0.5f;
-        r5 = (L.q[3] + r5) * 0.5f;
-        r6 = (L.q[4] + r6) * 0.25f;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            if (UF) r[c] = fmaf(a11, pb[c][1], fmaf(a10, pb[c][0], fmaf(a01, pt[c][1], a00 * pt[c][0])));
+            else r[c] = a00 * pt[c][0] + a01 * pt[c][1] + a10 * pb[c][0] + a11 * pb[c][1];
+        }
+        r[2] = (q[2] + r[2]) * 0.5f;
+        r[3] = (q[3] + r[3]) * 0.5f;
+        r[4] = (q[4] + r[4]) * 0.25f;
     } else {
-        r2 = r3 = 0.f;
-        r4 = L.q[2];
-        r5 = L.q[3];
-        r6 = L.q[4] * 0.5f;
+        r[0] = r[1] = 0.f;
+        r[2] = q[2];
+        r[3] = q[3];
+        r[4] = q[4] * 0.5f;
     }
-    r2 = (L.q[0] - r2) * 0.5f;
-    r3 = (L.q[1] - r3) * 0.5f;
-    r2 = r2 + (r4 * dy + r6 * dx);
-    r3 = r3 + (r6 * dy + r5 * dx);
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+    float r2 = (q[0] - r[0]) * 0.5f, r3 = (q[1] - r[1]) * 0.5f, r4 = r[2], r5 = r[3], r6 = r[4];
+    if (UF) {
+        r2 = fmaf(r4, dy, fmaf(r6, dx, r2));
+        r3 = fmaf(r6, dy, fmaf(r5, dx, r3));
+    } else {
+        r2 = r2 + (r4 * dy + r6 * dx);
+        r3 = r3 + (r6 * dy + r5 * dx);
+    }
+    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
         float sc = (x < 5 ? border_tab(x) : 1.f) * (x >= w - 5 ? border_tab(w - x - 1) : 1.f) * (y < 5 ? border_tab(y) : 1.f) *
                    (y >= h - 5 ? border_tab(h - y - 1) : 1.f);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
-    m[0] = r4 * r4 + r6 * r6;
-    m[1] = (r4 + r5) * r6;
-    m[2] = r5 * r5 + r6 * r6;
-    m[3] = r4 * r2 + r6 * r3;
-    m[4] = r6 * r2 + r5 * r3;
+    if (UF) {
+        const float r66 = r6 * r6;
+        m[0] = fmaf(r4, r4, r66);
+        m[1] = (r4 + r5) * r6;
+        m[2] = fmaf(r5, r5, r66);
+        m[3] = fmaf(r4, r2, r6 * r3);
+        m[4] = fmaf(r6, r2, r5 * r3);
+    } else {
+        m[0] = r4 * r4 + r6 * r6;
+        m[1] = (r4 + r5) * r6;
+        m[2] = r5 * r5 + r6 * r6;
+        m[3] = r4 * r2 + r6 * r3;
+        m[4] = r6 * r2 + r5 * r3;
+    }
 }
 
+template <bool UF>
+__device__ __forceinline__ void upd_compute(const UpdLoad &L, int w, int h, int x, int y, float dx, float dy, float m[5])
+{
+    float pt[5][2], pb[5][2];
+#pragma unroll
+    for (int c = 0; c < 5; c++) { pt[c][0] = L.p[c][0]; pt[c][1] = L.p[c][1]; pb[c][0] = L.p[c][2]; pb[c][1] = L.p[c][3]; }
+    upd_core<UF>(L.q, pt, pb, L.inside, L.fx, L.fy, w, h, x, y, dx, dy, m);
+}
+
+template <bool UF>
 __device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0, const float *__restrict__ R1,
                                                    int pitch, int w, int h, int x, int y, float dx, float dy, float m[5])
 {
     UpdLoad L;
     upd_load(R0, R1, pitch, w, h, x, y, dx, dy, L);
-    upd_compute(L, w, h, x, y, dx, dy, m);
+    upd_compute<UF>(L, w, h, x, y, dx, dy, m);
 }
 
 __device__ __forceinline__ void solve2x2(float g11f, float g12f, float g22f, float h1f, float h2f, float &fx, float &fy)
@@ -1084,7 +1111,7 @@ __device__ __forceinline__ void upsample_flow_px(const FirstUpdateArgs &a, int b
     dy = (t0 * gy + t1 * fy) * a.inv_scale;
 }
 
-template <int PITCH>
+template <int PITCH, bool UF>
 __global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
 {
     // one pixel per thread and <= 42 registers: 48 warps / SM keep enough loads in flight for this HBM-latency-bound
@@ -1109,7 +1136,7 @@ __global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
     if (a.M) {
         const float *R0 = a.R + (size_t)b * 10 * a.d.plane, *R1 = R0 + 5 * a.d.plane;
         float m[5];
-        update_matrices_px(R0, R1, a.d.pitch, a.d.w, a.d.h, x, y, dx, dy, m);
+        update_matrices_px<UF>(R0, R1, a.d.pitch, a.d.w, a.d.h, x, y, dx, dy, m);
         store_M(a.M + (size_t)b * 5 * a.d.plane, a.d.pitch, y, x, m);
     }
 }
@@ -1117,9 +1144,15 @@ __global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a)
 {
     dim3 grid((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.batch);
-    if (a.d.pitch == 2048) first_update_kernel<2048><<<grid, dim3(32, 8), 0, s>>>(a);
-    else if (a.d.pitch == 4096) first_update_kernel<4096><<<grid, dim3(32, 8), 0, s>>>(a);
-    else first_update_kernel<0><<<grid, dim3(32, 8), 0, s>>>(a);
+    if (a.ufma) {
+        if (a.d.pitch == 2048) first_update_kernel<2048, true><<<grid, dim3(32, 8), 0, s>>>(a);
+        else if (a.d.pitch == 4096) first_update_kernel<4096, true><<<grid, dim3(32, 8), 0, s>>>(a);
+        else first_update_kernel<0, true><<<grid, dim3(32, 8), 0, s>>>(a);
+    } else {
+        if (a.d.pitch == 2048) first_update_kernel<2048, false><<<grid, dim3(32, 8), 0, s>>>(a);
+        else if (a.d.pitch == 4096) first_update_kernel<4096, false><<<grid, dim3(32, 8), 0, s>>>(a);
+        else first_update_kernel<0, false><<<grid, dim3(32, 8), 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -1150,8 +1183,13 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
             if (gy >= h) continue;
             int gx = clampi(x0 - m + col, 0, w - 1) * es;
             float v = Mc[gy * rs + gx] * t.k[0];
-            for (int k = 1; k <= m; k++)
-                v = v + (Mc[min(gy + k, h - 1) * rs + gx] + Mc[max(gy - k, 0) * rs + gx]) * t.k[k];
+            if (a.fma == 2) {
+                for (int k = 1; k <= m; k++) { v = fmaf(Mc[max(gy - k, 0) * rs + gx], t.k[k], v); v = fmaf(Mc[min(gy + k, h - 1) * rs + gx], t.k[k], v); }
+            } else if (a.fma) {
+                for (int k = 1; k <= m; k++) v = fmaf(Mc[min(gy + k, h - 1) * rs + gx] + Mc[max(gy - k, 0) * rs + gx], t.k[k], v);
+            } else {
+                for (int k = 1; k <= m; k++) v = v + (Mc[min(gy + k, h - 1) * rs + gx] + Mc[max(gy - k, 0) * rs + gx]) * t.k[k];
+            }
             gi_smem[i] = v;
         }
         __syncthreads();
@@ -1160,7 +1198,13 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
             int col = tx + 32 * (j & 1), row = ty + 8 * (j >> 1);
             const float *p = gi_smem + row * SWD + col + m;
             float v = p[0] * t.k[0];
-            for (int k = 1; k <= m; k++) v = v + t.k[k] * (p[-k] + p[k]);
+            if (a.fma == 2) {
+                for (int k = 1; k <= m; k++) { v = fmaf(t.k[k], p[-k], v); v = fmaf(t.k[k], p[k], v); }
+            } else if (a.fma) {
+                for (int k = 1; k <= m; k++) v = fmaf(t.k[k], p[-k] + p[k], v);
+            } else {
+                for (int k = 1; k <= m; k++) v = v + t.k[k] * (p[-k] + p[k]);
+            }
             acc[c][j] = v;
         }
         __syncthreads();
@@ -1178,7 +1222,8 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
             f[o] = fx; f[o + plane] = fy;
         } else {
             float mm[5];
-            update_matrices_px(R0, R1, pitch, w, h, x, y, fx, fy, mm);
+            if (a.ufma) update_matrices_px<true>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
+            else update_matrices_px<false>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
             store_M(a.Mout + (size_t)b * 5 * plane, pitch, y, x, mm);
         }
     }
@@ -1198,7 +1243,55 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
 constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_RV = 16;
 constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
 
+#ifdef TW_TIMELINE // development builds only (tools/timeline.py): per-CTA phase timestamps of the level-0 window kernel
+__device__ unsigned long long g_timeline[16384 * 12];
+__device__ int g_tl_on;
+#define TW_TL_BEGIN(on) if (threadIdx.x == 0) g_tl_on = (on);
+#define TW_TL(slot)                                                                                              \
+    if (threadIdx.x == 0 && g_tl_on) {                                                                           \
+        const unsigned lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                    \
+        if (lin_ < 16384) {                                                                                      \
+            unsigned long long c_;                                                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c_));                                               \
+            g_timeline[lin_ * 12 + (slot)] = c_;                                                                 \
+            if ((slot) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_timeline[lin_ * 12 + 11] = sm_; } \
+        }                                                                                                        \
+    }
+#else
+#define TW_TL_BEGIN(on)
+#define TW_TL(slot)
+#endif
+
+// Per-pixel path of phase U for one thread's run of 4 vertically adjacent pixels (motion boundaries, frame borders,
+// partial tiles): two pixels' 2 x 25 loads in flight at a time.  Kept out of line so that its registers do not
+// weigh on the shared-row path.
+template <bool UF>
+__device__ __noinline__ void upd_run_slow(const float *__restrict__ R0, const float *__restrict__ R1, float *__restrict__ M,
+                                          const float *__restrict__ Fb, int pitch, int w, int h, int x, int yb, int rowb, int col)
+{
+#pragma unroll
+    for (int hf = 0; hf < 4; hf += 2) {
+        UpdLoad L[2];
+        bool ok[2];
+        float fxs[2], fys[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            ok[u] = x < w && yb + hf + u < h;
+            fxs[u] = Fb[(rowb + hf + u) * GK_FP + col]; fys[u] = Fb[(GK_TH + rowb + hf + u) * GK_FP + col];
+            if (ok[u]) upd_load(R0, R1, pitch, w, h, x, yb + hf + u, fxs[u], fys[u], L[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (!ok[u]) continue;
+            float mm[5];
+            upd_compute<UF>(L[u], w, h, x, yb + hf + u, fxs[u], fys[u], mm);
+            store_M(M, pitch, yb + hf + u, x, mm);
+        }
+    }
+}
+
 // phase U of K4/K5: lane = x, coalesced.  Last iteration: write the flow tile; otherwise the next update-matrices.
+template <bool UF>
 __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *__restrict__ Fb, int tid, int x0, int y0, int b, int pitch)
 {
     const int w = a.d.w, h = a.d.h;
@@ -1235,33 +1328,67 @@ __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *_
     }
     const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
     float *M = a.Mout + (size_t)b * 5 * plane;
-    // 12 pixels per thread, in 4 rounds of 3: all loads of a round are in flight together
+    // 12 pixels per thread: warp = 4 consecutive rows, lane = column of a 32-column chunk, 3 chunks.  A thread's 4
+    // vertically adjacent pixels usually gather from 5 consecutive R1 rows at one x1 (smooth flow): then the bottom
+    // row of pixel u IS the top row of pixel u+1 and the warp takes the shared-row path -- 50 + 20 loads for 4 pixels
+    // instead of 4 x 25, all in flight together, every address one base register + an immediate.  Any lane that does
+    // not fit (motion boundary, frame border, partial tile) sends its warp through the per-pixel path; both paths load
+    // the same values and run the same arithmetic.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int rowb = 4 * warp;
 #pragma unroll 1
-    for (int rnd = 0; rnd < 4; rnd++) {
-        UpdLoad L[3];
-        float fx[3], fy[3];
-        int xs[3], ys[3];
-        bool ok[3];
+    for (int k = 0; k < 3; k++) {
+        const int col = lane + 32 * k, x = x0 + col;
+        int yb = y0 + rowb;
+        asm volatile("" : "+r"(yb)); // opaque per chunk: keeps the row-only subexpressions (border scales, float rows) out of registers across the loop
+        // pass 1 (registers released before the loads): does every pixel of the run gather at (X1, Y1 + u)?
+        bool fast;
+        int X1, Y1;
+        {
+            int x1[4], y1[4];
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const int i = tid + (rnd * 3 + u) * 256;
-            const int row = i / GK_TW, col = i - row * GK_TW;
-            xs[u] = x0 + col; ys[u] = y0 + row;
-            ok[u] = xs[u] < w && ys[u] < h;
-            fx[u] = Fb[row * GK_FP + col]; fy[u] = Fb[(GK_TH + row) * GK_FP + col];
-            if (ok[u]) upd_load(R0, R1, pitch, w, h, xs[u], ys[u], fx[u], fy[u], L[u]);
+            for (int u = 0; u < 4; u++) {
+                const float px = (float)x + Fb[(rowb + u) * GK_FP + col], py = (float)(yb + u) + Fb[(GK_TH + rowb + u) * GK_FP + col];
+                x1[u] = __float2int_rd(px); y1[u] = __float2int_rd(py);
+            }
+            X1 = x1[0]; Y1 = y1[0];
+            // (also: no pixel of the run in the 5-pixel damped frame border, which implies x < w and yb + 3 < h)
+            fast = (unsigned)(x - 5) < (unsigned)(w - 10) && yb >= 5 && yb + 3 < h - 5 && (unsigned)X1 < (unsigned)(w - 1) && Y1 >= 0 &&
+                   Y1 + 4 < h && x1[1] == X1 && x1[2] == X1 && x1[3] == X1 && y1[1] == Y1 + 1 && y1[2] == Y1 + 2 && y1[3] == Y1 + 3;
         }
+        if (__all_sync(0xffffffffu, fast)) {
+            float q[4][5], rr[5][5][2];
+            const float *q0 = R0 + (size_t)yb * 5 * pitch + x;
+            const float *p = R1 + (size_t)Y1 * 5 * pitch + X1;
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
-            if (!ok[u]) continue;
-            float mm[5];
-            upd_compute(L[u], w, h, xs[u], ys[u], fx[u], fy[u], mm);
-            store_M(M, pitch, ys[u], xs[u], mm);
+            for (int r = 0; r < 5; r++)
+#pragma unroll
+                for (int c = 0; c < 5; c++) { rr[r][c][0] = __ldg(p + (r * 5 + c) * pitch); rr[r][c][1] = __ldg(p + (r * 5 + c) * pitch + 1); }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int c = 0; c < 5; c++) q[u][c] = __ldg(q0 + (u * 5 + c) * pitch);
+            // the flow is re-read from shared memory (through an opaque index, so that the values of pass 1 are not
+            // kept in registers under the 70 loads); x1 = X1 and y1 = Y1 + u here, hence the same fractions as pass 1
+            int col2 = col;
+            asm volatile("" : "+r"(col2));
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float fxu = Fb[(rowb + u) * GK_FP + col2], fyu = Fb[(GK_TH + rowb + u) * GK_FP + col2];
+                const float px = (float)x + fxu, py = (float)(yb + u) + fyu;
+                float mm[5];
+                upd_core<UF, false>(q[u], rr[u], rr[u + 1], true, px - (float)X1, py - (float)(Y1 + u), w, h, x, yb + u, fxu, fyu, mm);
+                store_M(M, pitch, yb + u, x, mm);
+                asm volatile("" ::: "memory"); // one pixel at a time: interleaving the four pixels' arithmetic costs more registers than there are
+            }
+        } else {
+            upd_run_slow<UF>(R0, R1, M, Fb, pitch, w, h, x, yb, rowb, col);
         }
+        TW_TL(4 + k)
     }
 }
 
-template <int MR, bool FMA, bool INTERIOR>
+template <int MR, int FMA, bool INTERIOR>
 __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, float *__restrict__ Vb, const WinTaps &t, int tid, int x0,
                                               int y0, int w, int h, int pitch, size_t plane)
 {
@@ -1288,7 +1415,8 @@ __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, flo
             float v = in[o + MR] * t.k[0];
 #pragma unroll
             for (int i = 1; i <= MR; i++) {
-                if (FMA) v = fmaf(in[o + MR + i] + in[o + MR - i], t.k[i], v);
+                if (FMA == 2) { v = fmaf(in[o + MR - i], t.k[i], v); v = fmaf(in[o + MR + i], t.k[i], v); }
+                else if (FMA) v = fmaf(in[o + MR + i] + in[o + MR - i], t.k[i], v);
                 else v = v + (in[o + MR + i] + in[o + MR - i]) * t.k[i];
             }
             dst[o * GK_VP] = v;
@@ -1296,7 +1424,7 @@ __device__ __forceinline__ void gauss_v_phase(const float *__restrict__ Min, flo
     }
 }
 
-template <int MR, bool FMA>
+template <int MR, int FMA, bool UF>
 __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps t)
 {
     extern __shared__ __align__(16) float gk_smem[];
@@ -1349,7 +1477,8 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
                     float s = v[ctr] * t.k[0];
 #pragma unroll
                     for (int i = 1; i <= MR; i++) {
-                        if (FMA) s = fmaf(t.k[i], v[ctr - i] + v[ctr + i], s);
+                        if (FMA == 2) { s = fmaf(t.k[i], v[ctr - i], s); s = fmaf(t.k[i], v[ctr + i], s); }
+                        else if (FMA) s = fmaf(t.k[i], v[ctr - i] + v[ctr + i], s);
                         else s = s + t.k[i] * (v[ctr - i] + v[ctr + i]);
                     }
                     res[c][p] = s;
@@ -1366,7 +1495,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     }
     __syncthreads();
 
-    gauss_epilogue(a, Fb, tid, x0, y0, b, pitch);
+    gauss_epilogue<UF>(a, Fb, tid, x0, y0, b, pitch);
 }
 
 
@@ -1420,7 +1549,7 @@ __device__ __forceinline__ float2 tw_fma2(float2 a, float2 b, float2 c)
 constexpr int G2_P2 = 130, G2_P4 = 132, G2_RV = 8;
 constexpr size_t G2_SMEM = sizeof(float) * (2 * GK_TH * G2_P2 * 2 + GK_TH * G2_P4 + 2 * GK_TH * GK_FP);
 
-template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
+template <int MR, int FMA, bool INTERIOR, bool CPITCH>
 __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
                                               int dstride, int ybase, int h, const WinTaps &t)
 {
@@ -1449,11 +1578,18 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
 #pragma unroll
     for (int i = 1; i <= MR; i++) {
         const float2 kk = make_float2(t.k[i], t.k[i]);
+        if (FMA == 2) { // direct form (oracle relax bit 7): upper tap first; no add -> fma dependency
 #pragma unroll
-        for (int o = 0; o < G2_RV; o++) {
-            const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
-            if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
-            else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]); // = v + round(sum * k): see tw_fma2 note
+            for (int o = 0; o < G2_RV; o++) v[o] = tw_fma2(in[o + MR - i], kk, v[o]);
+#pragma unroll
+            for (int o = 0; o < G2_RV; o++) v[o] = tw_fma2(in[o + MR + i], kk, v[o]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < G2_RV; o++) {
+                const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
+                if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
+                else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]); // = v + round(sum * k): see tw_fma2 note
+            }
         }
     }
 #pragma unroll
@@ -1464,7 +1600,7 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
 // window slides down by 8 rows per group; the 8 new rows of the next group are requested BEFORE the current group's
 // 8 x (1 + 3*MR) packed operations, so only the first window of a tile exposes load latency, and a tile column is
 // read 32+2*MR times instead of 4 x (8+2*MR).
-template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
+template <int MR, int FMA, bool INTERIOR, bool CPITCH>
 __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
                                               int dstride, int ybase, int h, const WinTaps &t)
 {
@@ -1496,11 +1632,18 @@ __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, in
 #pragma unroll
         for (int i = 1; i <= MR; i++) {
             const float2 kk = make_float2(t.k[i], t.k[i]);
+            if (FMA == 2) {
 #pragma unroll
-            for (int o = 0; o < G2_RV; o++) {
-                const float2 sum = tw_add2(win[o + MR + i], win[o + MR - i]);
-                if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
-                else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]);
+                for (int o = 0; o < G2_RV; o++) v[o] = tw_fma2(win[o + MR - i], kk, v[o]);
+#pragma unroll
+                for (int o = 0; o < G2_RV; o++) v[o] = tw_fma2(win[o + MR + i], kk, v[o]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < G2_RV; o++) {
+                    const float2 sum = tw_add2(win[o + MR + i], win[o + MR - i]);
+                    if (FMA) v[o] = tw_fma2(sum, kk, v[o]);
+                    else v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]);
+                }
             }
         }
 #pragma unroll
@@ -1518,7 +1661,7 @@ __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, in
 // (column pair jj, row group g) -- every item is "38 8-byte loads, 8 packed outputs".  Columns are replicated by
 // clamping the address; the h2 column pair is clamped as a pair (x0 and w are even multiples of the tile / pitch
 // except at the right edge, where both columns clamp to w-1 via the scalar fallback).
-template <int MR, bool FMA, bool INTERIOR, bool CPITCH>
+template <int MR, int FMA, bool INTERIOR, bool CPITCH>
 __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, float *__restrict__ sm, const WinTaps &t, int tid, int x0,
                                                int y0, int w, int h, int pitch, size_t plane)
 {
@@ -1533,6 +1676,7 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
         float2 *dst = (pair ? P23 : P01) + j;
         gauss_v_walk2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 - MR, h, t);
     }
+    TW_TL(1)
     {
         const int jj = tid & 63, g = tid >> 6;
         const int xa = x0 - 16 + 2 * jj;
@@ -1557,7 +1701,8 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
                 for (int i = 1; i <= MR; i++) {
                     const float2 sum = tw_add2(in[o + MR + i], in[o + MR - i]);
                     const float2 kk = make_float2(t.k[i], t.k[i]);
-                    if (FMA) v = tw_fma2(sum, kk, v);
+                    if (FMA == 2) v = tw_fma2(in[o + MR + i], kk, tw_fma2(in[o + MR - i], kk, v));
+                    else if (FMA) v = tw_fma2(sum, kk, v);
                     else v = tw_fma2(tw_mul2(sum, kk), one2, v);
                 }
                 dst[o * (G2_P4 / 2)] = v;
@@ -1568,7 +1713,8 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
 
 // PITCH > 0: the row pitch is a compile-time constant (the plan pads every level to 2048 or 4096 floats), so the
 // unrolled row addresses become LDG immediates instead of 3-4 integer instructions per load.
-template <int MR, bool FMA, int PITCH>
+
+template <int MR, int FMA, bool UF, int PITCH>
 __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps t)
 {
     extern __shared__ __align__(16) float gk_smem[];
@@ -1582,34 +1728,48 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
     // Every V item starts with a burst of loads whose latency is exposed (registers leave no room for double
     // buffering): pull the tile's M rows (all 5 planes, with halo) from DRAM into L2 up front, so that items 1..4 see
     // L2 latency; likewise the epilogue's R0 / R1 lines.
+    // (shift-only index arithmetic: this prologue runs while the co-resident CTA saturates the FMA pipe, which also
+    // executes IMAD -- the divisions of a flat index cost 7 % of a CTA's lifetime in the first version)
     {
-        constexpr int NR = GK_TH + 2 * MR, NL = 20; // rows x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
+        constexpr int NR = GK_TH + 2 * MR; // rows; per row 20 x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
         const int xl = max(x0 - 16, 0);
-        for (int i = tid; i < NR * NL; i += 256) {
-            const int row = i / NL, seg = i - row * NL;
-            const int y = clampi(y0 - MR + row, 0, h - 1);
-            const float *p;
-            const float *rowp = Min + (size_t)y * 5 * pitch;
-            if (seg < 16) p = rowp + (seg >> 3) * 2 * pitch + min(xl + (seg & 7) * 16, w - 1) * 2;
-            else p = rowp + 4 * pitch + min(xl + (seg - 16) * 32, w - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        const int row = tid >> 2, q = tid & 3; // 64 row slots x 4 threads, 5 lines each
+        if (row < NR) {
+            const float *rowp = Min + (size_t)clampi(y0 - MR + row, 0, h - 1) * 5 * pitch;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int seg = q * 5 + j;
+                const float *p;
+                if (seg < 16) p = rowp + (seg >> 3) * 2 * pitch + min(xl + (seg & 7) * 16, w - 1) * 2;
+                else p = rowp + 4 * pitch + min(xl + (seg - 16) * 32, w - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
         }
     }
     if (!a.last) {
         const float *Rb = a.R + (size_t)b * 10 * plane;
-        for (int i = tid; i < 10 * GK_TH * 3; i += 256) {
-            const int pl = i / (GK_TH * 3), rem = i - pl * (GK_TH * 3), row = rem / 3, seg = rem - row * 3;
-            const int y = min(y0 + row, h - 1), x = min(x0 + seg * 32, w - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl / 5) * 5 * plane + ((size_t)y * 5 + pl % 5) * pitch + x));
+        const int row = tid >> 3, u = tid & 7; // 32 rows x 8 threads; 30 lines per row (10 planes x 3 segments)
+        const int y = min(y0 + row, h - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = u + 8 * j;
+            if (idx < 30) {
+                const int pl = (idx * 11) >> 5, seg = idx - pl * 3; // idx / 3 for idx < 32
+                const int x = min(x0 + seg * 32, w - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl >= 5) * 5 * plane + ((size_t)y * 5 + (pl >= 5 ? pl - 5 : pl)) * pitch + x));
+            }
         }
     }
 
+    TW_TL_BEGIN(gridDim.x == 20 && !a.last)
+    TW_TL(0)
     // ---- phase V (packed) ----
     if ((y0 - MR >= 0) && (y0 + GK_TH + MR - 1 <= h - 1))
         gauss_v_phase2<MR, FMA, true, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
     else
         gauss_v_phase2<MR, FMA, false, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
     __syncthreads();
+    TW_TL(2)
 
     // ---- phase H (packed) + solve ----
     {
@@ -1640,12 +1800,19 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
 #pragma unroll
                 for (int i = 1; i <= MR; i++) {
                     const float2 kk = make_float2(t.k[i], t.k[i]);
+                    if (FMA == 2) { // direct form: left tap first
 #pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        const int ctr = p + 16 - LO;
-                        const float2 sum = tw_add2(v[ctr - i], v[ctr + i]);
-                        if (FMA) sacc[p] = tw_fma2(kk, sum, sacc[p]);
-                        else sacc[p] = tw_fma2(tw_mul2(kk, sum), one2, sacc[p]);
+                        for (int p = 0; p < 4; p++) sacc[p] = tw_fma2(kk, v[p + 16 - LO - i], sacc[p]);
+#pragma unroll
+                        for (int p = 0; p < 4; p++) sacc[p] = tw_fma2(kk, v[p + 16 - LO + i], sacc[p]);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            const int ctr = p + 16 - LO;
+                            const float2 sum = tw_add2(v[ctr - i], v[ctr + i]);
+                            if (FMA) sacc[p] = tw_fma2(kk, sum, sacc[p]);
+                            else sacc[p] = tw_fma2(tw_mul2(kk, sum), one2, sacc[p]);
+                        }
                     }
                 }
 #pragma unroll
@@ -1665,10 +1832,15 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
                     float2 sacc = tw_mul2(make_float2(v[ctr], v[ctr + 1]), make_float2(t.k[0], t.k[0]));
 #pragma unroll
                     for (int i = 1; i <= MR; i++) {
-                        const float2 sum = tw_add2(make_float2(v[ctr - i], v[ctr + 1 - i]), make_float2(v[ctr + i], v[ctr + 1 + i]));
                         const float2 kk = make_float2(t.k[i], t.k[i]);
-                        if (FMA) sacc = tw_fma2(kk, sum, sacc);
-                        else sacc = tw_fma2(tw_mul2(kk, sum), one2, sacc);
+                        if (FMA == 2) {
+                            sacc = tw_fma2(kk, make_float2(v[ctr - i], v[ctr + 1 - i]), sacc);
+                            sacc = tw_fma2(kk, make_float2(v[ctr + i], v[ctr + 1 + i]), sacc);
+                        } else {
+                            const float2 sum = tw_add2(make_float2(v[ctr - i], v[ctr + 1 - i]), make_float2(v[ctr + i], v[ctr + 1 + i]));
+                            if (FMA) sacc = tw_fma2(kk, sum, sacc);
+                            else sacc = tw_fma2(tw_mul2(kk, sum), one2, sacc);
+                        }
                     }
                     r4[p] = sacc.x; r4[p + 1] = sacc.y;
                 }
@@ -1683,55 +1855,79 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
         }
     }
     __syncthreads();
-    gauss_epilogue(a, Fb, tid, x0, y0, b, pitch);
+    TW_TL(3)
+    gauss_epilogue<UF>(a, Fb, tid, x0, y0, b, pitch);
+#ifdef TW_TIMELINE
+    __syncthreads();
+#endif
+    TW_TL(7)
 }
 
-template <int MR, bool FMA, int PITCH>
+template <int MR, int FMA, bool UF, int PITCH>
 static cudaError_t launch_gauss_fast2p(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
     static bool configured_dev[kMaxDevices] = {};
     bool &configured = configured_dev[current_device()];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA, UF, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
-    gauss_iter2_kernel<MR, FMA, PITCH><<<grid, 256, G2_SMEM, s>>>(a, t);
+    gauss_iter2_kernel<MR, FMA, UF, PITCH><<<grid, 256, G2_SMEM, s>>>(a, t);
     return cudaGetLastError();
 }
 
-template <int MR, bool FMA>
+template <int MR, int FMA, bool UF>
 static cudaError_t launch_gauss_fast2(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    if (a.d.pitch == 2048) return launch_gauss_fast2p<MR, FMA, 2048>(s, a, t);
-    if (a.d.pitch == 4096) return launch_gauss_fast2p<MR, FMA, 4096>(s, a, t);
-    return launch_gauss_fast2p<MR, FMA, 0>(s, a, t);
+    if (a.d.pitch == 2048) return launch_gauss_fast2p<MR, FMA, UF, 2048>(s, a, t);
+    if (a.d.pitch == 4096) return launch_gauss_fast2p<MR, FMA, UF, 4096>(s, a, t);
+    return launch_gauss_fast2p<MR, FMA, UF, 0>(s, a, t);
 }
 
-template <int MR, bool FMA>
+template <int MR, int FMA, bool UF>
 static cudaError_t launch_gauss_fast(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
     static bool configured_dev[kMaxDevices] = {};
     bool &configured = configured_dev[current_device()];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gauss_iter_kernel<MR, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GK_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gauss_iter_kernel<MR, FMA, UF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GK_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
-    gauss_iter_kernel<MR, FMA><<<grid, 256, GK_SMEM, s>>>(a, t);
+    gauss_iter_kernel<MR, FMA, UF><<<grid, 256, GK_SMEM, s>>>(a, t);
     return cudaGetLastError();
+}
+
+// (window mode, ufma) combinations that exist: faithful (0,0), the gauss_fma opt-in (1,0), relaxed = direct form (2,0),
+// relaxed + the update_fma opt-in (2,1).
+template <int MR>
+static cudaError_t launch_gauss_mr(cudaStream_t s, const IterArgs &a, const WinTaps &t)
+{
+#ifdef TW_DEV_ONE // development builds: one instantiation only (fast compile while tuning the kernel)
+    if (MR == 15 && a.d.pitch == 2048 && a.fma == 2 && !a.ufma) return launch_gauss_fast2p<15, 2, false, 2048>(s, a, t);
+    return cudaErrorNotSupported;
+#else
+    if (!a.scalar) {
+        if (a.fma == 2 && a.ufma) return launch_gauss_fast2<MR, 2, true>(s, a, t);
+        if (a.fma == 2) return launch_gauss_fast2<MR, 2, false>(s, a, t);
+        if (a.fma) return launch_gauss_fast2<MR, 1, false>(s, a, t);
+        return launch_gauss_fast2<MR, 0, false>(s, a, t);
+    }
+    if (a.fma == 2 && a.ufma) return launch_gauss_fast<MR, 2, true>(s, a, t);
+    if (a.fma == 2) return launch_gauss_fast<MR, 2, false>(s, a, t);
+    if (a.fma) return launch_gauss_fast<MR, 1, false>(s, a, t);
+    return launch_gauss_fast<MR, 0, false>(s, a, t);
+#endif
 }
 
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    if (!a.scalar) {
-        if (t.m == 15) return a.fma ? launch_gauss_fast2<15, true>(s, a, t) : launch_gauss_fast2<15, false>(s, a, t);
-        if (t.m == 7) return a.fma ? launch_gauss_fast2<7, true>(s, a, t) : launch_gauss_fast2<7, false>(s, a, t);
-    }
-    if (t.m == 15) return a.fma ? launch_gauss_fast<15, true>(s, a, t) : launch_gauss_fast<15, false>(s, a, t);
-    if (t.m == 7) return a.fma ? launch_gauss_fast<7, true>(s, a, t) : launch_gauss_fast<7, false>(s, a, t);
+    if (a.ufma && a.fma != 2) return cudaErrorInvalidValue;
+    if (t.m == 15) return launch_gauss_mr<15>(s, a, t);
+    if (t.m == 7) return launch_gauss_mr<7>(s, a, t);
     dim3 grid((a.d.w + GI_TW - 1) / GI_TW, (a.d.h + GI_TH - 1) / GI_TH, a.batch);
     size_t smem = sizeof(float) * GI_TH * (GI_TW + 2 * t.m);
     gauss_iter_generic_kernel<<<grid, 256, smem, s>>>(a, t);
@@ -1955,3 +2151,10 @@ cudaError_t launch_sample(cudaStream_t s, const SampleArgs &a)
 }
 
 } // namespace tw
+
+#ifdef TW_TIMELINE
+extern "C" int tw_debug_timeline(unsigned long long *out, int n_words)
+{
+    return (int)cudaMemcpyFromSymbol(out, tw::g_timeline, sizeof(unsigned long long) * n_words);
+}
+#endif

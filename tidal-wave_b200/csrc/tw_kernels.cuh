@@ -73,6 +73,7 @@ struct FirstUpdateArgs {
     float *flow_out; // [B][2] planes (nullptr: skip; used when pyrIterations == 0)
     LevelDims d;
     int batch;
+    int ufma; // validated relaxation: fmaf chains in the update-matrices arithmetic (oracle relax bit 6)
 };
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a);
 
@@ -92,7 +93,9 @@ struct IterArgs {
     double thr2;
     int *counts; // [B], zeroed by the host before the launch
     int scalar; // 1: scalar FP32 tap sums (v1 kernel) instead of packed f32x2
-    int fma; // validated relaxation: fmaf in the Gaussian tap sums (never set for the box window)
+    int fma; // Gaussian tap sums: 0 = oracle order (add, mul, add); validated relaxations: 1 = fmaf(a + b, k, t) (oracle relax
+             // bit 0), 2 = direct form fmaf(a, k, t), fmaf(b, k, t) (bit 7).  Never set for the box window.
+    int ufma; // validated relaxation: fmaf chains in the update-matrices arithmetic (oracle relax bit 6)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
 // Box window (flags == 0), App. A.6: vertical float-difference running sums in double (VT = V transposed,
