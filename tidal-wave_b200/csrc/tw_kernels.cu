@@ -1600,9 +1600,9 @@ __device__ __forceinline__ void gauss_v_item2(const float2 *__restrict__ src, in
 // window slides down by 8 rows per group; the 8 new rows of the next group are requested BEFORE the current group's
 // 8 x (1 + 3*MR) packed operations, so only the first window of a tile exposes load latency, and a tile column is
 // read 32+2*MR times instead of 4 x (8+2*MR).
-template <int MR, int FMA, bool INTERIOR, bool CPITCH>
+template <int MR, int FMA, bool INTERIOR, bool CPITCH, class PF>
 __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, int rstride /* float2 per row */, float2 *__restrict__ dst,
-                                              int dstride, int ybase, int h, const WinTaps &t)
+                                              int dstride, int ybase, int h, const WinTaps &t, PF &&after_first_loads)
 {
     constexpr int NIN = G2_RV + 2 * MR, NG = GK_TH / G2_RV;
     const float2 one2 = make_float2(t.one, t.one);
@@ -1619,6 +1619,7 @@ __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, in
     float2 win[NIN];
 #pragma unroll
     for (int r = 0; r < NIN; r++) win[r] = ld(r);
+    after_first_loads(); // the tile's L2 prefetches are issued under the latency of the first window
 #pragma unroll
     for (int g = 0; g < NG; g++) {
         float2 nxt[G2_RV];
@@ -1661,9 +1662,9 @@ __device__ __forceinline__ void gauss_v_walk2(const float2 *__restrict__ src, in
 // (column pair jj, row group g) -- every item is "38 8-byte loads, 8 packed outputs".  Columns are replicated by
 // clamping the address; the h2 column pair is clamped as a pair (x0 and w are even multiples of the tile / pitch
 // except at the right edge, where both columns clamp to w-1 via the scalar fallback).
-template <int MR, int FMA, bool INTERIOR, bool CPITCH>
+template <int MR, int FMA, bool INTERIOR, bool CPITCH, class PF>
 __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, float *__restrict__ sm, const WinTaps &t, int tid, int x0,
-                                               int y0, int w, int h, int pitch, size_t plane)
+                                               int y0, int w, int h, int pitch, size_t plane, PF &&after_first_loads)
 {
     float2 *P01 = reinterpret_cast<float2 *>(sm);
     float2 *P23 = P01 + GK_TH * G2_P2;
@@ -1674,7 +1675,7 @@ __device__ __forceinline__ void gauss_v_phase2(const float *__restrict__ Min, fl
         const int gx = clampi(x0 - 16 + j, 0, w - 1);
         const float2 *src = reinterpret_cast<const float2 *>(Min + pair * 2 * pitch) + gx;
         float2 *dst = (pair ? P23 : P01) + j;
-        gauss_v_walk2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 - MR, h, t);
+        gauss_v_walk2<MR, FMA, INTERIOR, CPITCH>(src, 5 * pitch / 2, dst, G2_P2, y0 - MR, h, t, after_first_loads);
     }
     TW_TL(1)
     {
@@ -1726,48 +1727,52 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
     const float *Min = a.Min + (size_t)b * 5 * plane;
 
     // Every V item starts with a burst of loads whose latency is exposed (registers leave no room for double
-    // buffering): pull the tile's M rows (all 5 planes, with halo) from DRAM into L2 up front, so that items 1..4 see
-    // L2 latency; likewise the epilogue's R0 / R1 lines.
-    // (shift-only index arithmetic: this prologue runs while the co-resident CTA saturates the FMA pipe, which also
-    // executes IMAD -- the divisions of a flat index cost 7 % of a CTA's lifetime in the first version)
-    {
-        constexpr int NR = GK_TH + 2 * MR; // rows; per row 20 x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
-        const int xl = max(x0 - 16, 0);
-        const int row = tid >> 2, q = tid & 3; // 64 row slots x 4 threads, 5 lines each
-        if (row < NR) {
-            const float *rowp = Min + (size_t)clampi(y0 - MR + row, 0, h - 1) * 5 * pitch;
+    // buffering).  The walker's first window goes to DRAM directly; UNDER that latency every thread then issues its share
+    // of L2 prefetches for the rest of the tile -- the M rows below the first window and the h2 plane (so that the later
+    // window refills and the h2 item see L2 latency) and the epilogue's R0 / R1 lines.
+    // (shift-only index arithmetic: this runs while the co-resident CTA saturates the FMA pipe, which also executes IMAD
+    // -- the divisions of a flat index cost 7 % of a CTA's lifetime in the first version)
+    auto prefetch_tile = [&]() {
+        {
+            constexpr int NR = GK_TH + 2 * MR; // rows; per row 20 x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
+            constexpr int NW = G2_RV + 2 * MR; // rows of the walkers' first window: their float2 planes are loaded, not prefetched
+            const int xl = max(x0 - 16, 0);
+            const int row = tid >> 2, q = tid & 3; // 64 row slots x 4 threads, 5 lines each
+            if (row < NR) {
+                const float *rowp = Min + (size_t)clampi(y0 - MR + row, 0, h - 1) * 5 * pitch;
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const int seg = q * 5 + j;
-                const float *p;
-                if (seg < 16) p = rowp + (seg >> 3) * 2 * pitch + min(xl + (seg & 7) * 16, w - 1) * 2;
-                else p = rowp + 4 * pitch + min(xl + (seg - 16) * 32, w - 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                for (int j = 0; j < 5; j++) {
+                    const int seg = q * 5 + j;
+                    const float *p;
+                    if (seg < 16) p = rowp + (seg >> 3) * 2 * pitch + min(xl + (seg & 7) * 16, w - 1) * 2;
+                    else p = rowp + 4 * pitch + min(xl + (seg - 16) * 32, w - 1);
+                    if (seg >= 16 || row >= NW) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
             }
         }
-    }
-    if (!a.last) {
-        const float *Rb = a.R + (size_t)b * 10 * plane;
-        const int row = tid >> 3, u = tid & 7; // 32 rows x 8 threads; 30 lines per row (10 planes x 3 segments)
-        const int y = min(y0 + row, h - 1);
+        if (!a.last) {
+            const float *Rb = a.R + (size_t)b * 10 * plane;
+            const int row = tid >> 3, u = tid & 7; // 32 rows x 8 threads; 30 lines per row (10 planes x 3 segments)
+            const int y = min(y0 + row, h - 1);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int idx = u + 8 * j;
-            if (idx < 30) {
-                const int pl = (idx * 11) >> 5, seg = idx - pl * 3; // idx / 3 for idx < 32
-                const int x = min(x0 + seg * 32, w - 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl >= 5) * 5 * plane + ((size_t)y * 5 + (pl >= 5 ? pl - 5 : pl)) * pitch + x));
+            for (int j = 0; j < 4; j++) {
+                const int idx = u + 8 * j;
+                if (idx < 30) {
+                    const int pl = (idx * 11) >> 5, seg = idx - pl * 3; // idx / 3 for idx < 32
+                    const int x = min(x0 + seg * 32, w - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl >= 5) * 5 * plane + ((size_t)y * 5 + (pl >= 5 ? pl - 5 : pl)) * pitch + x));
+                }
             }
         }
-    }
+    };
 
     TW_TL_BEGIN(gridDim.x == 20 && !a.last)
     TW_TL(0)
     // ---- phase V (packed) ----
     if ((y0 - MR >= 0) && (y0 + GK_TH + MR - 1 <= h - 1))
-        gauss_v_phase2<MR, FMA, true, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+        gauss_v_phase2<MR, FMA, true, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane, prefetch_tile);
     else
-        gauss_v_phase2<MR, FMA, false, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane);
+        gauss_v_phase2<MR, FMA, false, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane, prefetch_tile);
     __syncthreads();
     TW_TL(2)
 
