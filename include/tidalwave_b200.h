@@ -77,8 +77,10 @@ const char *tw_version(void);
 int tw_device_count(void);
 
 /* cv::imread(path, IMREAD_GRAYSCALE) on an in-memory file (src/opticalflow.cpp:37,44): PNG (non-interlaced, 8-bit; colour ->
- * gray exactly as OpenCV/libpng: (9797 R + 19234 G + 3737 B) >> 15) and binary PGM.  Host code, no device needed.  Call with
- * out == NULL to query *w, *h.  Anything else (JPEG, ...) -> TW_BAD_IMAGE_FORMAT, reported by callers as "Can't open <path>". */
+ * gray exactly as OpenCV/libpng: (9797 R + 19234 G + 3737 B) >> 15), JPEG (baseline / progressive Huffman, gray or YCbCr: the
+ * luma plane through libjpeg's ISLOW inverse DCT, as OpenCV's JCS_GRAYSCALE request does; EXIF orientation ignored like
+ * OpenCV 2.4.9) and binary PGM.  Host code, no device needed.  Call with out == NULL to query *w, *h.  Anything else ->
+ * TW_BAD_IMAGE_FORMAT, reported by callers as "Can't open <path>". */
 int tw_decode_gray(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap, int *w, int *h);
 
 /* ---- operator seam: OpticalFlow instance, one per consumer thread (src/consumer.cpp:27-35) ----

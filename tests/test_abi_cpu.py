@@ -65,7 +65,7 @@ def test_synth_is_deterministic(tw):
 
 def test_decode_gray_matches_cv2_fixtures(tw):
     """tw_decode_gray (row f-1): PNG colour types 0/2/3/6 -> gray bit-identical to cv2.imread(IMREAD_GRAYSCALE) (goldens made by
-    tools; the two fixture PNGs are the reference's own test files); JPEG and junk are 'empty images'."""
+    tools; the two fixture PNGs are the reference's own test files); junk is an 'empty image'."""
     import glob
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     n = 0
@@ -89,3 +89,72 @@ def test_decode_pgm_roundtrip(tw, tmp_path):
     assert np.array_equal(tw.imread_gray(str(p)), img)
     (tmp_path / "b.jpg").write_bytes(b"\xff\xd8\xff\xe0junk")
     assert tw.imread_gray(str(tmp_path / "b.jpg")) is None
+
+
+def test_decode_jpeg_matches_cv2_goldens(tw):
+    """tw_decode_gray, JPEG leg (row f-1): luma-only decode with libjpeg's ISLOW inverse DCT, bit-identical to
+    cv2.imread(IMREAD_GRAYSCALE) on the reference's own progressive scenario1 fixture and on baseline / progressive files in
+    every sampling (4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 / 4:1:1), with restart intervals, optimised tables, gray sources, 1x1
+    (goldens: tools/make_golden_jpeg.py)."""
+    import glob
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    img = tw.imread_gray(os.path.join(gold, "jpg", "fixture_s1_capture1.jpg"))
+    assert img is not None and img.shape == (279, 280)
+    assert np.array_equal(img, np.load(os.path.join(gold, "fixture_s1_expected.npy")))
+    n = 0
+    for jpg in sorted(glob.glob(os.path.join(gold, "jpg", "*.jpg"))):
+        ref = jpg[:-4] + ".gray.npy"
+        if os.path.exists(ref):
+            got = tw.imread_gray(jpg)
+            assert got is not None and np.array_equal(got, np.load(ref)), jpg
+            n += 1
+    assert n >= 11
+
+
+def test_decode_jpeg_rejects_what_it_cannot_match(tw, tmp_path):
+    """Truncated headers, arithmetic-coded / lossless frames and CMYK are 'empty images' (-> "Can't open <path>"), never guesses."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpg")
+    data = open(os.path.join(gold, "base_420_q75.jpg"), "rb").read()
+    sof = data.index(b"\xff\xc0")
+    for name, blob in (("cut_header", data[:sof + 6]), ("arith", data[:sof] + b"\xff\xc9" + data[sof + 2:]),
+                       ("lossless", data[:sof] + b"\xff\xc3" + data[sof + 2:]), ("no_scan", data[:data.index(b"\xff\xda")] + b"\xff\xd9"),
+                       ("four_comp", data[:sof + 9] + b"\x04" + data[sof + 10:])):
+        p = tmp_path / (name + ".jpg")
+        p.write_bytes(blob)
+        assert tw.imread_gray(str(p)) is None, name
+    # a file cut inside the entropy-coded data still decodes (missing data reads as zero bits, like libjpeg) to the full size
+    p = tmp_path / "cut_body.jpg"
+    p.write_bytes(data[:len(data) - 200])
+    got = tw.imread_gray(str(p))
+    assert got is not None and got.shape == (61, 83)
+
+
+def test_decode_jpeg_fuzz_vs_cv2(tw):
+    """Live comparison with cv2 (when importable) over random sizes / qualities / coding variants."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+    lib = tw.load()
+    rng = np.random.default_rng(7)
+    ss = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    for it in range(60):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if it % 3 == 0:
+            a = cv2.GaussianBlur(a, (5, 5), 1.5)
+        gray = it % 7 == 0
+        if gray:
+            a = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY)
+        params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 101)), cv2.IMWRITE_JPEG_PROGRESSIVE, int(rng.integers(0, 2)),
+                  cv2.IMWRITE_JPEG_OPTIMIZE, int(rng.integers(0, 2)), cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(0, 5))]
+        if not gray:
+            params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss[int(rng.integers(0, 5))]]
+        ok, enc = cv2.imencode(".jpg", a, params)
+        assert ok
+        ref = cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE)
+        data = enc.tobytes()
+        ww, hh = C.c_int(), C.c_int()
+        assert lib.tw_decode_gray(data, len(data), None, 0, C.byref(ww), C.byref(hh)) == 0 and (hh.value, ww.value) == ref.shape
+        out = np.empty(ref.shape, np.uint8)
+        assert lib.tw_decode_gray(data, len(data), out.ctypes.data, out.size, C.byref(ww), C.byref(hh)) == 0
+        assert np.array_equal(out, ref), (it, params)

@@ -1,6 +1,6 @@
 """File-level replay of /root/reference/test/index.coffee through the mirror of index.js (`create(targetDir, options)`): the
-directory pairing + lifecycle and the PNG / PGM decode (row f-1).  scenario2 uses the reference's own PNG files;
-scenario1 (a JPEG in the reference, not decodable bit-exactly here) is replayed from its decoded pixels as PGM."""
+directory pairing + lifecycle and the PNG / JPEG decode (row f-1).  Both scenarios use the reference's own
+fixture files: scenario2's PNGs and scenario1's progressive JPEG (byte-identical in all three revisions)."""
 import os
 import shutil
 
@@ -11,20 +11,14 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _pgm(path, img):
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    with open(path, "wb") as f:
-        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
-        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
-
-
 @pytest.fixture(scope="module")
 def fixture_tree(tmp_path_factory, golden):
     root = tmp_path_factory.mktemp("fixture")
     for rev, s2 in (("expected", "fixture_s2_expected.png"), ("revision1", "fixture_s2_expected.png"), ("revision2", "fixture_s2_revision2.png")):
         os.makedirs(root / rev / "scenario2", exist_ok=True)
         shutil.copy(os.path.join(GOLD, "png", s2), root / rev / "scenario2" / "capture2.png")
-        _pgm(str(root / rev / "scenario1" / "capture1.pgm"), golden["imgs"]["s1_expected"])
+        os.makedirs(root / rev / "scenario1", exist_ok=True)
+        shutil.copy(os.path.join(GOLD, "jpg", "fixture_s1_capture1.jpg"), root / rev / "scenario1" / "capture1.jpg")
     return root
 
 
@@ -45,8 +39,8 @@ def test_expect_dir(tw, golden, fixture_tree, rev):
         d.pop("time")
         if "capture1" in d["target_image"]:
             assert d == {"status": "OK", "span": 10, "threshold": 5, "height": 279, "width": 280, "vector": [],
-                         "expect_image": str(fixture_tree / "expected/scenario1/capture1.pgm"),
-                         "target_image": str(fixture_tree / rev / "scenario1/capture1.pgm")}
+                         "expect_image": str(fixture_tree / "expected/scenario1/capture1.jpg"),
+                         "target_image": str(fixture_tree / rev / "scenario1/capture1.jpg")}
         else:
             want = [c for c in golden["cases"] if c["revision"] == rev and c["width"] == 180][0]
             assert (d["status"], d["height"], d["width"], d["span"], d["threshold"]) == (want["status"], 117, 180, 10, 5)

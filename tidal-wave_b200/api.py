@@ -133,8 +133,9 @@ def declared_symbols() -> list[str]:
 
 
 def imread_gray(path: str):
-    """cv::imread(path, IMREAD_GRAYSCALE) (/root/reference/src/opticalflow.cpp:37,44) through tw_decode_gray: PNG / PGM.
-    Returns None (an "empty Mat") for a missing file or a format this build cannot decode bit-exactly (JPEG)."""
+    """cv::imread(path, IMREAD_GRAYSCALE) (/root/reference/src/opticalflow.cpp:37,44) through tw_decode_gray: PNG / JPEG / PGM.
+    Returns None (an "empty Mat") for a missing file or a format this build cannot decode bit-exactly (e.g. CMYK or
+    arithmetic-coded JPEG, interlaced or 16-bit PNG)."""
     try:
         data = open(path, "rb").read()
     except OSError:

@@ -9,7 +9,7 @@
 //   Observer<Response, std::string, Report>                     /root/reference/src/observer.h:10-18
 //
 // cv::Mat is replaced by two plain containers (Image = CV_8UC1, Plane = CV_32FC1); cv::imread by imread_gray()
-// (PNG and binary PGM via tw_decode_gray; JPEG is not decoded -- SURVEY row f-1).  uv_thread / uv_mutex / uv_cond become std::thread /
+// (PNG, JPEG and binary PGM via tw_decode_gray -- SURVEY row f-1).  uv_thread / uv_mutex / uv_cond become std::thread /
 // std::mutex / std::condition_variable; the uv_async hop to the V8 main loop does not exist: Manager::work calls the
 // observer directly.  There is no CPU operator: every consumer needs a CUDA device (id % device count).
 #pragma once

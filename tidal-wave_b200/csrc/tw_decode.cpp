@@ -6,8 +6,9 @@
 //        it through libpng (png_set_rgb_to_gray with 0.299 / 0.587): gray = (9797*R + 19234*G + 3737*B) >> 15,
 //        truncating (libpng turns 0.299 / 0.587 into the integers 29900*32768/100000 and 58700*32768/100000).  Verified bit-identical to cv2.imread(..., IMREAD_GRAYSCALE) on the reference's PNG fixtures.
 //   PGM  binary P5, maxval 255.
-//   JPEG is not decoded here (needs libjpeg's exact ISLOW IDCT): TW_BAD_IMAGE_FORMAT, which the callers report as
-//        "Can't open <path>" like a failed imread.
+//   JPEG baseline and progressive Huffman, gray or YCbCr: tw_jpeg.cpp (luma-only decode with libjpeg's ISLOW inverse DCT,
+//        bit-identical to cv2.imread(..., IMREAD_GRAYSCALE) on the reference's progressive scenario1 fixtures).
+//   Anything else: TW_BAD_IMAGE_FORMAT, which the callers report as "Can't open <path>" like a failed imread.
 #include "../../include/tidalwave_b200.h"
 
 #include <cstdlib>
@@ -127,11 +128,14 @@ int decode_png(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int
 
 } // namespace
 
+int tw_decode_jpeg_gray(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap, int *w, int *h); // tw_jpeg.cpp
+
 extern "C" int tw_decode_gray(const uint8_t *bytes, size_t n, uint8_t *out, size_t cap, int *w, int *h)
 {
     if (!bytes || !w || !h) return TW_BAD_PARAMETER;
     static const uint8_t png_sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
     if (n >= 8 && !memcmp(bytes, png_sig, 8)) return decode_png(bytes, n, out, cap, w, h);
     if (n >= 2 && bytes[0] == 'P' && bytes[1] == '5') return decode_pgm(bytes, n, out, cap, w, h);
+    if (n >= 2 && bytes[0] == 0xFF && bytes[1] == 0xD8) return tw_decode_jpeg_gray(bytes, n, out, cap, w, h);
     return TW_BAD_IMAGE_FORMAT;
 }

@@ -2,7 +2,7 @@
 
 Mirrors /root/reference/index.js:14-73 (directory pairing + lifecycle) and the option parsing of
 Broker::createInstance (/root/reference/src/broker.cpp:101-123, typed defaults :106-117, wrong-typed keys silently fall back
-to the default :190-209) on top of the dispatcher (tw_pool_*).  Files are decoded with ``imread_gray`` (PNG / PGM,
+to the default :190-209) on top of the dispatcher (tw_pool_*).  Files are decoded with ``imread_gray`` (PNG / JPEG / PGM,
 bit-exact to cv::imread IMREAD_GRAYSCALE); a file that cannot be decoded becomes the reference's "Can't open <path>" error.
 """
 from __future__ import annotations
