@@ -1244,8 +1244,9 @@ constexpr int GK_TW = 96, GK_TH = 32, GK_VW = 128, GK_VP = 132, GK_FP = 97, GK_R
 constexpr size_t GK_SMEM = sizeof(float) * (5 * GK_TH * GK_VP + 2 * GK_TH * GK_FP);
 
 #ifdef TW_TIMELINE // development builds only (tools/timeline.py): per-CTA phase timestamps of the level-0 window kernel
-__device__ unsigned long long g_timeline[16384 * 12];
+__device__ unsigned long long g_timeline[16384 * 24];
 __device__ int g_tl_on;
+__device__ int g_dev_flags; // experiments: 1 = no R prefetch, 2 = no M prefetch, 4 = R prefetch at the start of phase H, 8 = no U sub-stamps
 #define TW_TL_BEGIN(on) if (threadIdx.x == 0) g_tl_on = (on);
 #define TW_TL(slot)                                                                                              \
     if (threadIdx.x == 0 && g_tl_on) {                                                                           \
@@ -1253,13 +1254,19 @@ __device__ int g_tl_on;
         if (lin_ < 16384) {                                                                                      \
             unsigned long long c_;                                                                               \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c_));                                               \
-            g_timeline[lin_ * 12 + (slot)] = c_;                                                                 \
-            if ((slot) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_timeline[lin_ * 12 + 11] = sm_; } \
+            g_timeline[lin_ * 24 + (slot)] = c_;                                                                 \
+            if ((slot) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_timeline[lin_ * 24 + 23] = sm_; } \
         }                                                                                                        \
     }
+#define TW_TL_DEP(slot, dep)                                                                                     \
+    { float d_ = (dep); asm volatile("" ::"f"(d_) : "memory"); }                                                 \
+    TW_TL(slot)
+#define TW_DEV_FLAG(bit) (g_dev_flags & (bit))
 #else
 #define TW_TL_BEGIN(on)
 #define TW_TL(slot)
+#define TW_TL_DEP(slot, dep)
+#define TW_DEV_FLAG(bit) 0
 #endif
 
 // Per-pixel path of phase U for one thread's run of 4 vertically adjacent pixels (motion boundaries, frame borders,
@@ -1357,6 +1364,7 @@ __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *_
                    Y1 + 4 < h && x1[1] == X1 && x1[2] == X1 && x1[3] == X1 && y1[1] == Y1 + 1 && y1[2] == Y1 + 2 && y1[3] == Y1 + 3;
         }
         if (__all_sync(0xffffffffu, fast)) {
+            if (!TW_DEV_FLAG(8)) { TW_TL(8 + 4 * k) } // after the vote
             float q[4][5], rr[5][5][2];
             const float *q0 = R0 + (size_t)yb * 5 * pitch + x;
             const float *p = R1 + (size_t)Y1 * 5 * pitch + X1;
@@ -1370,6 +1378,7 @@ __device__ __forceinline__ void gauss_epilogue(const IterArgs &a, const float *_
                 for (int c = 0; c < 5; c++) q[u][c] = __ldg(q0 + (u * 5 + c) * pitch);
             // the flow is re-read from shared memory (through an opaque index, so that the values of pass 1 are not
             // kept in registers under the 70 loads); x1 = X1 and y1 = Y1 + u here, hence the same fractions as pass 1
+            if (!TW_DEV_FLAG(8)) { TW_TL_DEP(9 + 4 * k, q[3][4] + rr[4][4][1] + rr[0][0][0]) } // last-issued and first-issued loads have arrived
             int col2 = col;
             asm volatile("" : "+r"(col2));
 #pragma unroll
@@ -1732,8 +1741,22 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
     // window refills and the h2 item see L2 latency) and the epilogue's R0 / R1 lines.
     // (shift-only index arithmetic: this runs while the co-resident CTA saturates the FMA pipe, which also executes IMAD
     // -- the divisions of a flat index cost 7 % of a CTA's lifetime in the first version)
+    auto prefetch_R = [&]() {
+        const float *Rb = a.R + (size_t)b * 10 * plane;
+        const int row = tid >> 3, u = tid & 7; // 32 rows x 8 threads; 30 lines per row (10 planes x 3 segments)
+        const int y = min(y0 + row, h - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = u + 8 * j;
+            if (idx < 30) {
+                const int pl = (idx * 11) >> 5, seg = idx - pl * 3; // idx / 3 for idx < 32
+                const int x = min(x0 + seg * 32, w - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl >= 5) * 5 * plane + ((size_t)y * 5 + (pl >= 5 ? pl - 5 : pl)) * pitch + x));
+            }
+        }
+    };
     auto prefetch_tile = [&]() {
-        {
+        if (!TW_DEV_FLAG(2)) {
             constexpr int NR = GK_TH + 2 * MR; // rows; per row 20 x 128-byte lines: 8 + 8 (float2 planes) + 4 (float plane)
             constexpr int NW = G2_RV + 2 * MR; // rows of the walkers' first window: their float2 planes are loaded, not prefetched
             const int xl = max(x0 - 16, 0);
@@ -1750,20 +1773,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
                 }
             }
         }
-        if (!a.last) {
-            const float *Rb = a.R + (size_t)b * 10 * plane;
-            const int row = tid >> 3, u = tid & 7; // 32 rows x 8 threads; 30 lines per row (10 planes x 3 segments)
-            const int y = min(y0 + row, h - 1);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int idx = u + 8 * j;
-                if (idx < 30) {
-                    const int pl = (idx * 11) >> 5, seg = idx - pl * 3; // idx / 3 for idx < 32
-                    const int x = min(x0 + seg * 32, w - 1);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Rb + (size_t)(pl >= 5) * 5 * plane + ((size_t)y * 5 + (pl >= 5 ? pl - 5 : pl)) * pitch + x));
-                }
-            }
-        }
+        if (!a.last && !TW_DEV_FLAG(1) && !TW_DEV_FLAG(4)) prefetch_R();
     };
 
     TW_TL_BEGIN(gridDim.x == 20 && !a.last)
@@ -1775,6 +1785,7 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
         gauss_v_phase2<MR, FMA, false, (PITCH > 0)>(Min, gk_smem, t, tid, x0, y0, w, h, pitch, plane, prefetch_tile);
     __syncthreads();
     TW_TL(2)
+    if (!a.last && TW_DEV_FLAG(4)) prefetch_R();
 
     // ---- phase H (packed) + solve ----
     {
@@ -1861,6 +1872,10 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
     }
     __syncthreads();
     TW_TL(3)
+    // (Tried and measured slower, 2.73 vs 2.33 ms per step: staging the tile's R1 gather window -- 5 x 39 x 104 floats centred
+    // on the tile's mean flow -- in the 83 KB the dead planes leave, with 16-byte coalesced loads and the corners read by
+    // LDS.  The extra barrier and the exposed window load cost more than the gathers save, because phase U is paced by
+    // the co-resident CTA's hold on the FMA pipe / issue slots rather than by its own loads)
     gauss_epilogue<UF>(a, Fb, tid, x0, y0, b, pitch);
 #ifdef TW_TIMELINE
     __syncthreads();
@@ -2158,6 +2173,7 @@ cudaError_t launch_sample(cudaStream_t s, const SampleArgs &a)
 } // namespace tw
 
 #ifdef TW_TIMELINE
+extern "C" int tw_debug_set_flags(int flags) { return (int)cudaMemcpyToSymbol(tw::g_dev_flags, &flags, sizeof(int)); }
 extern "C" int tw_debug_timeline(unsigned long long *out, int n_words)
 {
     return (int)cudaMemcpyFromSymbol(out, tw::g_timeline, sizeof(unsigned long long) * n_words);
