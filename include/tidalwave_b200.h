@@ -132,13 +132,16 @@ const char *tw_last_error(tw_ctx *ctx);
  *                     oracle/farneback_ref.c on every configuration.
  *                = 1 (default; TW_ARITHMETIC=faithful in the environment or tw_set_default_arithmetic(0) flips it):
  *                     relaxed arithmetic where it was validated -- Gaussian window (flags 256) with winSize >= 30 and
- *                     polyN 7, i.e. the reference's default option family: fmaf in the window tap sums and a mixed
- *                     double / float horizontal pass in the polynomial expansion.  Measured against the faithful oracle
- *                     and cv2: <= 2.6e-4 px at 1920x1080, 2.1e-3 px max / 1.2e-4 px RMS on the reference's fixture,
- *                     identical status and vector sets (bar: 1e-2 px max, 1e-3 px RMS; tools/relax_study.py).  Every
- *                     other option set (box window, smaller windows, polyN != 7) runs the faithful kernels.
+ *                     polyN 7, i.e. the reference's default option family: direct-form fmaf window taps and a mixed
+ *                     double / float horizontal pass in the polynomial expansion (restated bit for bit in the oracle:
+ *                     twref_set_relax(144)).  Measured against the faithful oracle and cv2: <= 1.5e-4 px at 1920x1080,
+ *                     2.3e-3 px max / 1.3e-4 px RMS on the reference's fixture, identical status and vector sets (bar:
+ *                     1e-2 px max, 1e-3 px RMS; tools/relax_cases.py, tools/parity_report.py).  Every other option set
+ *                     (box window, smaller windows, polyN != 7) runs the faithful kernels.
  *   "graph"      = 1 (default): repeated runs of one (size, batch, options) replay a captured CUDA graph.
- *   "gauss_fma"  = 1: fmaf in the Gaussian window tap sums only (part of "arithmetic" = 1).
+ *   "gauss_fma"  = 1: symmetric fmaf in the Gaussian window tap sums on top of the faithful arithmetic (oracle relax bit 0).
+ *   "update_fma" = 1: fmaf chains in the update matrices on top of "arithmetic" = 1 (oracle relax bit 6; studied, rejected
+ *                     as a default: 0.157 px on the reference's scenario1 fixture).
  *   "gauss_scalar", "level_generic", "level_unfused", "tight_pitch": alternative code paths kept for the parity tests. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);
 /* Process-wide default of "arithmetic" for contexts created afterwards (the dispatcher's consumers included). */
