@@ -158,3 +158,21 @@ def test_decode_jpeg_fuzz_vs_cv2(tw):
         out = np.empty(ref.shape, np.uint8)
         assert lib.tw_decode_gray(data, len(data), out.ctypes.data, out.size, C.byref(ww), C.byref(hh)) == 0
         assert np.array_equal(out, ref), (it, params)
+
+
+def test_decode_fuzz_sanitizers(tmp_path):
+    """Mutated PNG / JPEG goldens through tw_decode_gray under ASan + UBSan (tests/cpp/fuzz_decode.cpp): no out-of-bounds access,
+    no undefined shift, nothing thrown across the C ABI."""
+    import glob, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fuzz_decode")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17",
+                           "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "fuzz_decode.cpp"),
+                           os.path.join(root, "tidal-wave_b200", "csrc", "tw_jpeg.cpp"), os.path.join(root, "tidal-wave_b200", "csrc", "tw_decode.cpp"),
+                           "-lz", "-o", exe])
+    files = sorted(glob.glob(os.path.join(root, "tests", "golden", "jpg", "*.jpg")) + glob.glob(os.path.join(root, "tests", "golden", "png", "*.png")))
+    out = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "runs" in out.stdout

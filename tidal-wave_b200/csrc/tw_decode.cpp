@@ -134,8 +134,12 @@ extern "C" int tw_decode_gray(const uint8_t *bytes, size_t n, uint8_t *out, size
 {
     if (!bytes || !w || !h) return TW_BAD_PARAMETER;
     static const uint8_t png_sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
-    if (n >= 8 && !memcmp(bytes, png_sig, 8)) return decode_png(bytes, n, out, cap, w, h);
-    if (n >= 2 && bytes[0] == 'P' && bytes[1] == '5') return decode_pgm(bytes, n, out, cap, w, h);
-    if (n >= 2 && bytes[0] == 0xFF && bytes[1] == 0xD8) return tw_decode_jpeg_gray(bytes, n, out, cap, w, h);
+    try { // nothing may propagate across the C ABI (a hostile header can ask for gigabytes: std::bad_alloc)
+        if (n >= 8 && !memcmp(bytes, png_sig, 8)) return decode_png(bytes, n, out, cap, w, h);
+        if (n >= 2 && bytes[0] == 'P' && bytes[1] == '5') return decode_pgm(bytes, n, out, cap, w, h);
+        if (n >= 2 && bytes[0] == 0xFF && bytes[1] == 0xD8) return tw_decode_jpeg_gray(bytes, n, out, cap, w, h);
+    } catch (...) {
+        return TW_BAD_IMAGE_FORMAT;
+    }
     return TW_BAD_IMAGE_FORMAT;
 }

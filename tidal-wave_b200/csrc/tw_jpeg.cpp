@@ -402,6 +402,8 @@ struct Decoder {
                         int cnt = 0;
                         for (int i = 1; i <= 16; i++) { bits[i] = d[o + i]; cnt += bits[i]; }
                         if (th > 3 || tc > 1 || cnt > 256 || o + 17 + cnt > dl) return TW_BAD_IMAGE_FORMAT;
+                        if (tc == 0) // DC symbols are magnitude categories: libjpeg rejects tables with any > 15
+                            for (int i = 0; i < cnt; i++) if (d[o + 17 + i] > 15) return TW_BAD_IMAGE_FORMAT;
                         (tc ? ac[th] : dc[th]).build(bits, d + o + 17, cnt);
                         o += 17 + cnt;
                     }
