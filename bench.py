@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--arithmetic", default="default", choices=["default", "faithful"],
                     help="default = the library default (relaxed where validated: include/tidalwave_b200.h); faithful = the "
                          "oracle's operation order everywhere (bit-identical results)")
+    ap.add_argument("--last", default="sparse", choices=["sparse", "dense"],
+                    help="last iteration of the finest scale: 'sparse' = evaluated at the sampled positions only (what the dispatcher "
+                         "does: the Response carries vectors, not the field; bit-identical vectors), 'dense' = full flow field")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -182,6 +185,8 @@ def main():
     if args.arithmetic == "faithful":
         tw.set_default_arithmetic(False)  # contexts created from here on, the e2e pool's consumers included
     of = tw.OpticalFlow(local_rank, W, H, B)
+    of.set_option("sparse_last", 1 if args.last == "sparse" else 0)
+    os.environ["TW_SPARSE_LAST"] = "1" if args.last == "sparse" else "0"  # the e2e pool's consumers
     param = tw.OpticalFlowParameter()
     arithmetic = of.arithmetic_in_effect(param)
     cp = param.c()
@@ -330,10 +335,26 @@ def main():
         of.set_option("arithmetic", 1 - other)
         notes = {"faithful": "tw_set_option(arithmetic, 0): every kernel in the oracle's operation order, results bit-identical to "
                              "oracle/farneback_ref.c and <= 1.2e-7 px from cv2 on this workload",
-                 "relaxed": "tw_set_option(arithmetic, 1): fmaf window taps + mixed double/float poly-exp pass; <= 2.6e-4 px from "
+                 "relaxed": "tw_set_option(arithmetic, 1): direct-form fmaf window taps + mixed double/float poly-exp pass; <= 1.5e-4 px from "
                             "the faithful oracle at 1920x1080, status / vectors identical"}
         variants = {other_name: {"value": tw.dist.whole_job_throughput(B * nv, world, o_ms * 1e-3), "unit": UNIT,
                                  "ms_per_step": o_ms / nv, "note": notes[other_name]}}
+        # the other form of the last iteration, same arithmetic as the headline
+        of.set_option("sparse_last", 0 if args.last == "sparse" else 1)
+        for _ in range(3):
+            step()
+        check(lib.tw_sync(of.ctx), "sync")
+        barrier()
+        check(lib.tw_timer_start(of.ctx), "timer")
+        for _ in range(nv):
+            step()
+        check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")
+        l_ms = dist.reduce_max(float(ms.value))
+        of.set_option("sparse_last", 1 if args.last == "sparse" else 0)
+        lname = "dense_last_iteration" if args.last == "sparse" else "sparse_last_iteration"
+        variants[lname] = {"value": tw.dist.whole_job_throughput(B * nv, world, l_ms * 1e-3), "unit": UNIT, "ms_per_step": l_ms / nv,
+                           "note": ("the whole flow field is produced (tw_flow / tw_batch_flow callers); identical vectors and status"
+                                    if args.last == "sparse" else "blur + solve of the last iteration at the sampled positions only")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -354,6 +375,10 @@ def main():
                                           "double/float horizontal poly-exp pass; measured <= 1.5e-4 px from the faithful oracle at "
                                           "1920x1080 (bar 1e-2), status and vectors identical; tests/test_gpu_relaxed.py")
                            if arithmetic == "relaxed" else "faithful: the oracle's operation order, bit-identical results",
+                           "last_iteration": ("sparse: the finest scale's last blur + solve runs only at the positions the reference samples "
+                                              "(src/consumer.cpp:60-77), as in the dispatcher -- the Response carries vectors and status, never "
+                                              "the field; vectors bit-identical to the dense path (tests/test_gpu_sparse_last.py); the dense form "
+                                              "is timed in variants.dense_last_iteration") if args.last == "sparse" else "dense: full flow field",
                            "launch": "one CUDA graph replay per step (%d kernel nodes)" % (launches // max(args.steps, 1)),
                            "parallelism": "independent pairs per GPU, no collective",
                            "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2"},

@@ -124,7 +124,8 @@ int tw_batch_run(tw_ctx *ctx, int n, int w, int h, const tw_flow_param *param, d
                  int span);                                                  /* enqueue all kernels, no sync */
 int tw_batch_fetch(tw_ctx *ctx, int n, tw_vector *out, int cap, tw_result *res); /* D2H compact results + sync */
 int tw_sync(tw_ctx *ctx);
-/* Copies the dense flow planes of pair `pair` of the last run back (either pointer may be NULL). */
+/* Copies the dense flow planes of pair `pair` of the last run back (either pointer may be NULL); TW_BAD_PARAMETER if that run
+ * was classification-only ("sparse_last"). */
 int tw_batch_flow(tw_ctx *ctx, int pair, float *flowx, float *flowy);
 const char *tw_last_error(tw_ctx *ctx);
 /* Per-context options.
@@ -138,6 +139,11 @@ const char *tw_last_error(tw_ctx *ctx);
  *                     2.3e-3 px max / 1.3e-4 px RMS on the reference's fixture, identical status and vector sets (bar:
  *                     1e-2 px max, 1e-3 px RMS; tools/relax_cases.py, tools/parity_report.py).  Every other option set
  *                     (box window, smaller windows, polyN != 7) runs the faithful kernels.
+ *   "sparse_last" = 1: classification only -- the last iteration of the finest scale evaluates the window blur and the solve
+ *                     only at the positions src/consumer.cpp:60-77 samples (Gaussian window of radius 15 / 7, span > 0).  Status
+ *                     and vectors (positions and the float dx, dy) are bit-identical to the dense path; the dense flow field
+ *                     is not produced (tw_batch_flow fails after such a run; tw_flow is always dense).  Default 0 for
+ *                     tw_create, 1 for the dispatcher's contexts (tw_pool_*; TW_SPARSE_LAST=0 turns it off there).
  *   "graph"      = 1 (default): repeated runs of one (size, batch, options) replay a captured CUDA graph.
  *   "gauss_fma"  = 1: symmetric fmaf in the Gaussian window tap sums on top of the faithful arithmetic (oracle relax bit 0).
  *   "update_fma" = 1: fmaf chains in the update matrices on top of "arithmetic" = 1 (oracle relax bit 6; studied, rejected

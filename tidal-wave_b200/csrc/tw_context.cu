@@ -59,6 +59,8 @@ struct tw_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_r0 = nullptr, ev_r1 = nullptr;
     Plan plan;
     int keep_levels = 0;
+    int opt_sparse_last = 0; // 1: last iteration of the finest scale only at the span-grid points (no dense flow field)
+    bool last_sparse = false; // the previous run left no dense field
     int opt_update_fma = 0; // studied opt-in (oracle relax bit 6), never part of "arithmetic" = 1
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
     int opt_arith = 1;  // 0 = faithful (App. A operation order), 1 = relaxed where validated (relaxed_in_effect)
@@ -482,6 +484,17 @@ bool relaxed_in_effect(const tw_ctx *ctx, const tw_flow_param &p)
     return ctx->opt_arith == 1 && (p.flags & 256) && p.winSize >= 30 && p.polyN == 7;
 }
 
+// Whether a run with this span ends in the sparse last iteration (K5s): then no dense flow field exists afterwards.
+bool sparse_in_effect(const tw_ctx *ctx, int span)
+{
+    const Plan &pl = ctx->plan;
+    const tw_flow_param &p = pl.p;
+    if (!(span > 0 && ctx->opt_sparse_last && (p.flags & 256) && p.pyrIterations > 0 && (pl.win.m == 15 || pl.win.m == 7))) return false;
+    IterArgs ia{};
+    ia.span = span;
+    return gauss_last_sparse_ok(ia, pl.win);
+}
+
 // The launch sequence for n pairs already resident in plan.src.  SURVEY App. A.1 / A.7.
 bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
 {
@@ -551,7 +564,10 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             ia.ufma = (ia.fma == 2 && ctx->opt_update_fma) ? 1 : 0;
             ia.scalar = ctx->opt_gauss_scalar;
             double bytes = n * (ia.last ? 28 : 80) * Pl;
-            if (p.flags & 256) {
+            if (ia.span > 0 && sparse_in_effect(ctx, span)) {
+                // classification only: blur + solve at the sampled positions (one pass over M, no flow plane written)
+                LAUNCH(F_GLAST, n * 20.0 * Pl, launch_gauss_last_sparse(ctx->stream, ia, pl.win));
+            } else if (p.flags & 256) {
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
             } else {
                 LAUNCH(F_BVSUM, 0.0, launch_box_vsum(ctx->stream, Min, pl.V, s.d, n, p.winSize / 2));
@@ -587,7 +603,7 @@ bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
     if (!ctx->opt_graph || ctx->profiling) return enqueue(ctx, n, threshold, span);
     tw_ctx::GraphKey key;
     key.plan_gen = ctx->plan_gen; key.n = n; key.thr = threshold; key.span = span;
-    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5;
+    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5 | ctx->opt_sparse_last << 6;
     key.vectors = ctx->d_vectors;
     if (ctx->graph_exec && key == ctx->graph_key) {
         cudaError_t e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
@@ -844,6 +860,7 @@ int tw_batch_run(tw_ctx *ctx, int n, int w, int h, const tw_flow_param *param, d
     if (!run_sequence(ctx, n, threshold, span)) return TW_CUDA_ERROR;
     cudaEventRecord(ctx->ev_r1, ctx->stream);
     ctx->last_n = n; ctx->last_w = w; ctx->last_h = h; ctx->ran = true;
+    ctx->last_sparse = sparse_in_effect(ctx, span);
     return TW_OK;
 }
 
@@ -884,6 +901,7 @@ int tw_batch_fetch(tw_ctx *ctx, int n, tw_vector *out, int cap, tw_result *res)
 int tw_batch_flow(tw_ctx *ctx, int pair, float *flowx, float *flowy)
 {
     if (!ctx || !ctx->ran || pair < 0 || pair >= ctx->last_n) return TW_BAD_PARAMETER;
+    if (ctx->last_sparse) { ctx->err = "no dense flow: the last run used \"sparse_last\" (classification only)"; return TW_BAD_PARAMETER; }
     cudaSetDevice(ctx->device);
     const Scale &f = ctx->plan.scales.back();
     const float *base = f.flow + (size_t)pair * 2 * f.d.plane;
@@ -1042,6 +1060,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "arithmetic")) { ctx->opt_arith = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "graph")) { ctx->opt_graph = value ? 1 : 0; if (!value) drop_graph(ctx); return TW_OK; }
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "sparse_last")) { ctx->opt_sparse_last = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "update_fma")) { ctx->opt_update_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }

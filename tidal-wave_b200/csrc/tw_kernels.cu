@@ -1955,6 +1955,107 @@ cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5s  LAST iteration of the FINEST scale when only the classification is wanted (the dispatcher path: the reference's
+//      Response carries the sampled vectors, never the dense field -- src/consumer.cpp:59-88, src/message_queue.h:27-40).
+//      The window blur + 2x2 solve are evaluated only where src/consumer.cpp:60-77 samples the flow: rows y = j * span get
+//      the vertical pass at every column, the horizontal pass + solve run at the columns x = i * span only.  Same operand
+//      order as the dense kernels in each arithmetic (IterArgs::fma), so the sampled (dx, dy) -- written at their positions
+//      of the flow planes, where sample_kernel picks them up -- are bit-identical to the dense path; the rest of the planes
+//      is NOT produced (tw_batch_flow refuses after such a run).  FP work drops ~16x; what remains is one pass over M.
+//      One CTA = one sampled row x (256 - 2m) columns; thread = column (all five channels, 2m + 1 rows in registers' reach);
+//      then (sample, channel) threads walk the taps in the oracle's order; then one thread per sample solves and tests.
+// ------------------------------------------------------------------------------------------------
+constexpr int SP_THREADS = 256, SP_MAXS = 64; // SP_MAXS: most samples one CTA can own (span >= 4 with m = 0 .. )
+
+__global__ void __launch_bounds__(SP_THREADS) gauss_last_sparse_kernel(IterArgs a, WinTaps t)
+{
+    __shared__ float sv[5][SP_THREADS];
+    __shared__ float sb[SP_MAXS][5];
+    const int m = t.m, tw_cols = SP_THREADS - 2 * m;
+    const int tid = threadIdx.x, b = blockIdx.z;
+    const int x0 = blockIdx.x * tw_cols, y = blockIdx.y * a.span;
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const float *Min = a.Min + (size_t)b * 5 * a.d.plane;
+    // ---- vertical pass at row y, column gx (replicated past the frame like App. A.5) ----
+    {
+        const int gx = clampi(x0 - m + tid, 0, w - 1);
+        const size_t rs = (size_t)5 * pitch;
+        const float *c01 = Min + 2 * gx, *c23 = Min + 2 * pitch + 2 * gx, *c4 = Min + 4 * pitch + gx;
+        float v[5];
+        {
+            const float2 p = __ldg(reinterpret_cast<const float2 *>(c01 + y * rs)), q = __ldg(reinterpret_cast<const float2 *>(c23 + y * rs));
+            const float r = __ldg(c4 + y * rs), k0 = t.k[0];
+            v[0] = __fmul_rn(p.x, k0); v[1] = __fmul_rn(p.y, k0); v[2] = __fmul_rn(q.x, k0); v[3] = __fmul_rn(q.y, k0); v[4] = __fmul_rn(r, k0);
+        }
+#pragma unroll 5
+        for (int i = 1; i <= m; i++) {
+            const size_t od = (size_t)min(y + i, h - 1) * rs, ou = (size_t)max(y - i, 0) * rs;
+            const float2 pd = __ldg(reinterpret_cast<const float2 *>(c01 + od)), pu = __ldg(reinterpret_cast<const float2 *>(c01 + ou));
+            const float2 qd = __ldg(reinterpret_cast<const float2 *>(c23 + od)), qu = __ldg(reinterpret_cast<const float2 *>(c23 + ou));
+            const float rd = __ldg(c4 + od), ru = __ldg(c4 + ou), k = t.k[i];
+            const float dn[5] = {pd.x, pd.y, qd.x, qd.y, rd}, up[5] = {pu.x, pu.y, qu.x, qu.y, ru};
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                if (a.fma == 2) { v[c] = fmaf(up[c], k, v[c]); v[c] = fmaf(dn[c], k, v[c]); }
+                else if (a.fma == 1) v[c] = fmaf(__fadd_rn(dn[c], up[c]), k, v[c]);
+                else v[c] = __fadd_rn(v[c], __fmul_rn(__fadd_rn(dn[c], up[c]), k));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) sv[c][tid] = v[c];
+    }
+    __syncthreads();
+    // ---- horizontal pass at the sampled columns of this CTA: x = i * span in [x0, min(x0 + tw_cols, w)) ----
+    const int s0 = (x0 + a.span - 1) / a.span;
+    const int ns = max(0, (min(x0 + tw_cols, w) - 1) / a.span - s0 + 1);
+    for (int idx = tid; idx < ns * 5; idx += SP_THREADS) {
+        const int s = idx / 5, c = idx - s * 5;
+        const float *p = &sv[c][(s0 + s) * a.span - x0 + m];
+        float r = __fmul_rn(p[0], t.k[0]);
+        for (int i = 1; i <= m; i++) {
+            const float k = t.k[i];
+            if (a.fma == 2) { r = fmaf(k, p[-i], r); r = fmaf(k, p[i], r); }
+            else if (a.fma == 1) r = fmaf(k, __fadd_rn(p[-i], p[i]), r);
+            else r = __fadd_rn(r, __fmul_rn(k, __fadd_rn(p[-i], p[i])));
+        }
+        sb[s][c] = r;
+    }
+    __syncthreads();
+    int hit = 0;
+    if (tid < ns) {
+        float fx, fy;
+        solve2x2(sb[tid][0], sb[tid][1], sb[tid][2], sb[tid][3], sb[tid][4], fx, fy);
+        const int x = (s0 + tid) * a.span;
+        float *f = a.flow + (size_t)b * 2 * a.d.plane + (size_t)y * pitch + x;
+        f[0] = fx; f[a.d.plane] = fy;
+        const float len = __fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy));
+        hit = ((double)len > a.thr2) ? 1 : 0;
+    }
+    if (tid < 64) { // ns <= SP_MAXS = 64: two warps cover every sample
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) hit += __shfl_xor_sync(0xffffffffu, hit, off);
+        if ((tid & 31) == 0 && hit > 0) atomicAdd(a.counts + b, hit);
+    }
+}
+
+// Applicable when the samples of a CTA fit its table and the window fits the CTA: else the caller runs the dense kernel.
+bool gauss_last_sparse_ok(const IterArgs &a, const WinTaps &t)
+{
+    if (a.span < 1 || t.m < 0 || 2 * t.m + 32 > SP_THREADS) return false;
+    const int cols = SP_THREADS - 2 * t.m;
+    return (cols + a.span - 1) / a.span + 1 <= SP_MAXS;
+}
+
+cudaError_t launch_gauss_last_sparse(cudaStream_t s, const IterArgs &a, const WinTaps &t)
+{
+    if (!gauss_last_sparse_ok(a, t)) return cudaErrorInvalidValue;
+    const int cols = SP_THREADS - 2 * t.m;
+    dim3 grid((a.d.w + cols - 1) / cols, (a.d.h + a.span - 1) / a.span, a.batch);
+    gauss_last_sparse_kernel<<<grid, SP_THREADS, 0, s>>>(a, t);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Box window (flags == 0), App. A.6.  Both running sums are evaluated in the oracle's order, because the
 // regularised 2x2 solve amplifies even 1e-16-relative re-association differences on screenshot content
 // (measured: a direct window sum moved config 4 by up to 0.12 px on 3e-5 of the pixels).

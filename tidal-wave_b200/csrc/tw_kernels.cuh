@@ -98,6 +98,10 @@ struct IterArgs {
     int ufma; // validated relaxation: fmaf chains in the update-matrices arithmetic (oracle relax bit 6)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
+// K5s: last iteration of the finest scale evaluated only at the span-grid points (needs a.span, a.thr2, a.counts; writes the
+// sampled (dx, dy) at their positions of a.flow and nothing else).  gauss_last_sparse_ok: whether this geometry is supported.
+bool gauss_last_sparse_ok(const IterArgs &a, const WinTaps &t);
+cudaError_t launch_gauss_last_sparse(cudaStream_t s, const IterArgs &a, const WinTaps &t);
 // Box window (flags == 0), App. A.6: vertical float-difference running sums in double (VT = V transposed,
 // [B*5][w][roundup(h,32)] doubles), then the horizontal running sum + solve -> flow; the next update-matrices
 // is launch_first_update with flow_in.

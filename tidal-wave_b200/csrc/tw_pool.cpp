@@ -80,6 +80,13 @@ void consumer_main(tw_pool *p, int idx)
 {
     char err[256] = {0};
     tw_ctx *ctx = tw_create(p->devices[idx], p->max_w, p->max_h, p->batch, err, sizeof err);
+    // The dispatcher only ever reports status + sampled vectors (Response, src/message_queue.h:27-40): its contexts evaluate
+    // the last iteration of the finest scale at the sampled positions only (bit-identical vectors, no dense field).
+    // TW_SPARSE_LAST=0 keeps the dense last iteration.
+    if (ctx) {
+        const char *e = getenv("TW_SPARSE_LAST");
+        tw_set_option(ctx, "sparse_last", (e && atoi(e) == 0) ? 0 : 1);
+    }
     {
         std::lock_guard<std::mutex> lk(p->mu);
         if (!ctx) p->init_error = err;
