@@ -11,8 +11,8 @@ python tools/parity_report.py > $o/${tag}_parity_fullsize.jsonl 2> $o/${tag}_par
 export TW_GRAPH=0
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
 $CMD > $o/${tag}_plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_batch16.csv $CMD > $o/${tag}_ncu_launches.log 2>&1; echo "launch list rc=$?"
-$CMD > $o/${tag}_plain2.log 2>&1 && ncu --set full --clock-control none -k regex:"gauss_iter2|polyexp|first_update|level_" -s 63 -c 21 -o /tmp/prof_${tag} $CMD > $o/${tag}_ncu_full.log 2>&1; echo "full rc=$?"
+$CMD > $o/${tag}_plain2.log 2>&1 && ncu --set full --clock-control none -k regex:"gauss_iter2|gauss_last_sparse|polyexp|first_update|level_" -s 63 -c 21 -o /tmp/prof_${tag} $CMD > $o/${tag}_ncu_full.log 2>&1; echo "full rc=$?"
 python tools/ncu_summary.py /tmp/prof_${tag}.ncu-rep $o/${tag}_ncu_full_step_batch16.csv
 python tools/ncu_traffic.py $o/${tag}_ncu_full_step_batch16.csv 16 relaxed > $o/${tag}_traffic.json
-$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_iter2" -s 36 -c 3 -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
+$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_iter2" -s 42 -c 1 -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
 ls -la $o | grep ${tag}
