@@ -25,17 +25,28 @@ const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+constexpr int kLookBits = 9;
+
 struct Huff {
     bool present = false;
     int mincode[17], maxcode[18], valptr[17];
     uint8_t vals[256];
+    uint16_t look[1 << kLookBits]; // (length << 8) | symbol for codes of at most kLookBits bits, 0 = longer code
     void build(const uint8_t *bits /* [1..16] */, const uint8_t *v, int n)
     {
+        memset(vals, 0, sizeof vals);
         memcpy(vals, v, n);
+        memset(look, 0, sizeof look);
         int code = 0, k = 0;
         for (int l = 1; l <= 16; l++) {
             valptr[l] = k;
             mincode[l] = code;
+            if (l <= kLookBits)
+                for (int i = 0; i < bits[l]; i++) {
+                    const int first = (code + i) << (kLookBits - l);
+                    if (first + (1 << (kLookBits - l)) > (1 << kLookBits)) break; // over-subscribed table: the slow path handles it
+                    for (int j = 0; j < (1 << (kLookBits - l)); j++) look[first + j] = (uint16_t)((l << 8) | vals[(k + i) & 255]);
+                }
             k += bits[l];
             code += bits[l];
             maxcode[l] = bits[l] ? code - 1 : -1;
@@ -86,6 +97,8 @@ struct BitReader {
         return v;
     }
     int bit() { return bits(1); }
+    int peek(int n) { if (cnt < n) fill(); return (int)(buf >> (32 - n)); }
+    void skip(int n) { buf <<= n; cnt -= n; }
     // byte-align and consume an RSTn marker if one is next
     void restart()
     {
@@ -102,6 +115,8 @@ inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 :
 
 int decode_symbol(BitReader &br, const Huff &h)
 {
+    const int e = h.look[br.peek(kLookBits)];
+    if (e) { br.skip(e >> 8); return e & 255; }
     int code = br.bit(), l = 1;
     while (code > h.maxcode[l]) {
         if (++l > 16) return 0; // corrupt data: libjpeg warns and returns 0
