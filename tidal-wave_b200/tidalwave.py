@@ -42,6 +42,7 @@ class TidalWave:
         self._batch = batch
         self._pool = None
         self._disposed = False
+        self._decoders = None  # numThreads decode workers: the reference decodes inside its consumer threads (src/consumer.cpp:54)
 
     # EventEmitter
     def on(self, event, fn):
@@ -72,19 +73,38 @@ class TidalWave:
             self._pending.append((None, expected, target, "ExpectImagePath is empty.")); return
         if not target:
             self._pending.append((None, expected, target, "TargetImagePath is empty.")); return
+        if self._decoders is None:
+            from concurrent.futures import ThreadPoolExecutor
+            from .api import load
+            load()  # bind the library on this thread before the workers use it
+            self._decoders = ThreadPoolExecutor(max_workers=max(1, self.numThreads))
+        # the two imreads run on a decode worker (tw_decode_gray releases the GIL); the pair is queued once both are in
+        self._pending.append((self._decoders.submit(self._decode_pair, expected, target), expected, target, None))
+
+    @staticmethod
+    def _decode_pair(expected, target):
+        """The imread half of OpticalFlow::calculate (src/opticalflow.cpp:37-49): (expect, target, None) or (None, None, message)."""
         a = imread_gray(expected)
         if a is None:
-            self._pending.append((None, expected, target, "Can't open " + expected)); return
+            return None, None, "Can't open " + expected
         b = imread_gray(target)
         if b is None:
-            self._pending.append((None, expected, target, "Can't open " + target)); return
-        pool = self._ensure_pool(max(a.shape[1], b.shape[1]), max(a.shape[0], b.shape[0]))
-        self._pending.append((pool.request(a, b), expected, target, None))
+            return None, None, "Can't open " + target
+        return a, b, None
 
     def flush(self):
         """Delivers every outstanding answer as 'data' / 'error' events (the uv_async hop of src/manager.cpp:102-125)."""
         pending, self._pending = self._pending, []
-        for rid, expected, target, err in pending:
+        queued = []
+        for fut, expected, target, err in pending:  # request order: decoded pairs go to the dispatcher as they become ready
+            rid = None
+            if err is None:
+                a, b, err = fut.result()
+                if err is None:
+                    pool = self._ensure_pool(max(a.shape[1], b.shape[1]), max(a.shape[0], b.shape[0]))
+                    rid = pool.request(a, b)
+            queued.append((rid, expected, target, err))
+        for rid, expected, target, err in queued:
             if err is None:
                 r = self._pool.wait(rid)
                 if r is None:
@@ -106,6 +126,9 @@ class TidalWave:
             return
         self.flush()
         self._disposed = True
+        if self._decoders is not None:
+            self._decoders.shutdown(wait=True)
+            self._decoders = None
         if self._pool is not None:
             self._pool.stop()
             self._pool.close()
