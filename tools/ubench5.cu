@@ -142,5 +142,10 @@ int main()
     run("stream PF=4, 66.5 KB", k_stream4, sm_v, M, out, pitch, plane5, t, grid);
     run("stream PF=8, 66.5 KB", k_stream8, sm_v, M, out, pitch, plane5, t, grid);
     run("stream PF=4, 108 KB (2/SM)", k_stream4, 108288, M, out, pitch, plane5, t, grid);
+    // the same passes on 2 pairs only: the 71 MB they read stay L2-resident between the timed launches (DRAM out of the picture)
+    dim3 g2(20, 32, 2);
+    run("L2-resident: window, 108 KB", k_window, 108288, M, out, pitch, plane5, t, g2);
+    run("L2-resident: window, 66.5 KB", k_window, sm_v, M, out, pitch, plane5, t, g2);
+    run("L2-resident: stream PF=4", k_stream4, sm_v, M, out, pitch, plane5, t, g2);
     return 0;
 }
