@@ -68,13 +68,13 @@ struct Component {
 
 struct BitReader {
     const uint8_t *p, *end;
-    uint32_t buf = 0;
+    uint64_t buf = 0; // bits left-aligned
     int cnt = 0;
     bool hit_marker = false;
     BitReader(const uint8_t *b, const uint8_t *e) : p(b), end(e) {}
     void fill()
     {
-        while (cnt <= 24) {
+        while (cnt <= 56) {
             int c = 0;
             if (!hit_marker && p < end) {
                 c = *p;
@@ -83,7 +83,7 @@ struct BitReader {
                     else { hit_marker = true; c = 0; } // a marker: feed zeros from here on, like libjpeg does
                 } else p++;
             }
-            buf |= (uint32_t)c << (24 - cnt);
+            buf |= (uint64_t)c << (56 - cnt);
             cnt += 8;
         }
     }
@@ -91,13 +91,13 @@ struct BitReader {
     {
         if (n == 0) return 0;
         if (cnt < n) fill();
-        int v = (int)(buf >> (32 - n));
+        int v = (int)(buf >> (64 - n));
         buf <<= n;
         cnt -= n;
         return v;
     }
     int bit() { return bits(1); }
-    int peek(int n) { if (cnt < n) fill(); return (int)(buf >> (32 - n)); }
+    int peek(int n) { if (cnt < n) fill(); return (int)(buf >> (64 - n)); }
     void skip(int n) { buf <<= n; cnt -= n; }
     // byte-align and consume an RSTn marker if one is next
     void restart()
@@ -142,6 +142,8 @@ struct RangeLimit {
     }
 };
 const RangeLimit kRange;
+const uint16_t kEndianProbe = 1;
+const bool kLittleEndian = *reinterpret_cast<const uint8_t *>(&kEndianProbe) == 1;
 
 void idct_islow(const int16_t *in, const uint16_t *q, uint8_t *out, int stride)
 {
@@ -494,7 +496,19 @@ struct Decoder {
         uint8_t px[64];
         for (int by = 0; by < c.hblk; by++) {
             for (int bx = 0; bx < c.wblk; bx++) {
-                idct_islow(block(c, bx, by), qt[c.tq], px, 8);
+                const int16_t *blk = block(c, bx, by);
+                // DC-only block (most of a screenshot): both passes of the inverse DCT take their zero-AC shortcuts, the block is
+                // the constant range_limit(descale(dc * q0 << PASS1_BITS, PASS1_BITS + 3)) -- same value, 64 multiplies saved
+                uint64_t ac[16];
+                memcpy(ac, blk, sizeof ac);
+                uint64_t any = ac[0] & ~(uint64_t)0xFFFF; // little-endian: coefficient 0 is the low half-word
+                for (int i = 1; i < 16; i++) any |= ac[i];
+                if (!any && kLittleEndian) {
+                    const int64_t dc = (int64_t)((int32_t)blk[0] * qt[c.tq][0]) * (1 << kPass1Bits);
+                    memset(px, kRange.t[descale(dc, kPass1Bits + 3) & 1023], 64);
+                } else {
+                    idct_islow(blk, qt[c.tq], px, 8);
+                }
                 const int ys = by * 8, xs = bx * 8;
                 for (int y = 0; y < 8 && ys + y < H; y++) {
                     const int cols = W - xs < 8 ? W - xs : 8;
