@@ -2,7 +2,7 @@
 // through the C++ mirror of its Manager / Consumer / OpticalFlow classes (tidalwave_host.hpp) on top of the C ABI.
 // usage: test_host <numThreads> <expect.pgm> <target.pgm> [<expect.pgm> <target.pgm> ...]
 // Prints one JSON line per response / error, then the report.
-#include "../../tidal-wave_b200/csrc/tidalwave_host.hpp"
+#include "tidalwave_host.hpp"
 
 using namespace tidalwave;
 

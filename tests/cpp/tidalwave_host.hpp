@@ -1,5 +1,8 @@
-// tidalwave_host.hpp -- host side ABOVE the C ABI, mirroring the reference's C++ operator / worker / manager classes
-// with the same names, argument meaning and error behaviour, minus OpenCV / libuv / V8 (absent in this image):
+// tidalwave_host.hpp -- TEST SCAFFOLDING (not product code, not a component): a REFERENCE-DERIVED host above the C ABI.
+// It re-creates the reference's C++ operator / worker / manager class shapes (same names, argument meaning and error
+// behaviour, minus OpenCV / libuv / V8, which are absent in this image) so that tests/cpp/test_host.cpp can replay
+// /root/reference/test/index.coffee against libtidalwave_b200.so the way a maintainer's integration would call it.
+// The product's dispatcher is tidal-wave_b200/csrc/tw_pool.cpp; nothing in the library includes this file.
 //
 //   OpticalFlowParameter, OpticalFlowStatus, ErrorCode, OpticalFlow::calculate / calculateInternal
 //                                              /root/reference/src/opticalflow.h:9-52, src/opticalflow.cpp:20-94
@@ -256,46 +259,48 @@ public:
     }
     ~Consumer() { stop(); delete opticalFlow; }
 
-    int run() // src/consumer.cpp:42-94
+    // What the worker loop of src/consumer.cpp:42-94 does, expressed over the C ABI's result types: pop, compute, answer.
+    int run()
     {
+        Request req;
         while (isRunning) {
-            Request req;
-            if (requestQueue.tryPop(req)) {
-                Plane flowx, flowy;
-                OpticalFlowStatus status = opticalFlow->calculate(req.expect_image, req.target_image, parameter, flowx, flowy);
-                Response res;
-                if (status.code == OK) {
-                    for (int y = 0; y < flowx.rows; ++y) {
-                        if (y % req.span != 0) continue;
-                        for (int x = 0; x < flowx.cols; ++x) {
-                            if (x % req.span != 0) continue;
-                            float dx = flowx.at(y, x);
-                            float dy = flowy.at(y, x);
-                            float len = (dx * dx) + (dy * dy);
-                            if (len > (req.threshold * req.threshold)) {
-                                Vector v;
-                                v.x = x; v.y = y; v.dx = dx; v.dy = dy;
-                                res.vectors.push_back(v);
-                            }
-                        }
-                    }
-                    res.status = res.vectors.size() == 0 ? "OK" : "SUSPICIOUS";
-                    res.time = status.time;
-                    res.expect_image = req.expect_image;
-                    res.target_image = req.target_image;
-                    res.span = req.span;
-                    res.threshold = req.threshold;
-                    res.height = status.height;
-                    res.width = status.width;
-                } else {
-                    res.status = "ERROR";
-                    res.reason = status.message;
-                }
-                responseQueue.push(res);
-            }
+            if (!requestQueue.tryPop(req)) continue;
+            responseQueue.push(answer(req));
         }
         return 0;
     }
+
+private:
+    // sampling rule of src/consumer.cpp:60-77: every span-th row / column, float len, strict double compare
+    static void sampleVectors(const Plane &fx, const Plane &fy, int span, double threshold, std::vector<Vector> &out)
+    {
+        const double limit = threshold * threshold;
+        for (int y = 0; y < fx.rows; y += span)
+            for (int x = 0; x < fx.cols; x += span) {
+                const float dx = fx.at(y, x), dy = fy.at(y, x);
+                const float len = (dx * dx) + (dy * dy);
+                if (len > limit) out.push_back(Vector{x, y, dx, dy});
+            }
+    }
+    Response answer(const Request &req)
+    {
+        Response res;
+        Plane flowx, flowy;
+        const OpticalFlowStatus st = opticalFlow->calculate(req.expect_image, req.target_image, parameter, flowx, flowy);
+        if (st.code != OK) { // src/consumer.cpp:85-88
+            res.status = "ERROR";
+            res.reason = st.message;
+            return res;
+        }
+        sampleVectors(flowx, flowy, req.span, req.threshold, res.vectors);
+        res.status = res.vectors.empty() ? "OK" : "SUSPICIOUS";
+        res.expect_image = req.expect_image; res.target_image = req.target_image;
+        res.span = req.span; res.threshold = req.threshold;
+        res.time = st.time; res.height = st.height; res.width = st.width;
+        return res;
+    }
+
+public:
     void start(const OpticalFlowParameter &param)
     {
         parameter = param;

@@ -1,5 +1,5 @@
 """The reference's own integration test (/root/reference/test/index.coffee:12-117) replayed through the C++ mirror of its
-Manager / Consumer / OpticalFlow classes (tidal-wave_b200/csrc/tidalwave_host.hpp) on top of the C ABI."""
+Manager / Consumer / OpticalFlow classes (tests/cpp/tidalwave_host.hpp) on top of the C ABI."""
 import json
 import os
 import subprocess
