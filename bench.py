@@ -7,14 +7,19 @@ A "step" = one pass of the whole hot path (pyramid, polynomial expansion, update
 iterations, span sampling + classification) over one batch of B synthetic 1920x1080 pairs with the reference's
 default options (BASELINE.json configs[1]; the batch is configs[4]'s work-queue unit).
 
-  value     pairs/s with the batch already resident in HBM (device pass only, CUDA events on the library's stream; the
-            launch sequence of a step replays as one captured CUDA graph, as it does for every API caller)
-  e2e       pairs/s through the dispatcher API (tw_pool_*): pinned HOST images in, result structs out, H2D/D2H inside
-  roofline  dominant kernel family: algorithmic bytes / event-timed duration vs measured HBM peak
+  value         pairs/s with the batch already resident in HBM (device pass only, CUDA events on the library's stream; the
+                launch sequence of a step replays as one captured CUDA graph, as it does for every API caller)
+  e2e           BASELINE configs[4]: 10,000 pairs cycled from 64 distinct pinned HOST pairs through the dispatcher API
+                (tw_pool_submit / tw_pool_wait), H2D + compute + D2H of the compact results inside the timed region
+  roofline      dominant kernel family: algorithmic bytes / event-timed duration vs measured HBM peak
+  variants      the other arithmetic / last-iteration forms of the same step (faithful, dense, faithful + dense)
+  configs       BASELINE configs[2] (3840x2160, 5 levels, 5 iterations) and configs[3] (1280x2000 box window) device-resident,
+                each against its own algorithmic-byte roofline; configs[4] is the e2e leg
   cpu_baseline  the reference's CPU path (cv2 calcOpticalFlowFarneback, else the C oracle port) on this box's cores
 
 Multi-GPU: pairs are independent => each rank runs its own shard (weak scaling), no data-path collective; torch.distributed
-is used only for the barrier and the max-over-ranks of the timed region.
+is used only for the barrier and the max-over-ranks of the timed region.  At N > 1 rank 0 additionally drives ONE in-process
+dispatcher over all N GPUs (e2e_inprocess: the reference's Manager + Consumers shape) while the other ranks idle.
 """
 from __future__ import annotations
 
@@ -24,7 +29,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -36,6 +40,11 @@ if ROOT not in sys.path:
 W, H = 1920, 1080
 METRIC = "image pairs/sec at 1920x1080"
 UNIT = "pairs/s"
+# the SAME string in both arms (the driver compares config.workload)
+WORKLOAD = ("configs[1]/[4]: synthetic 1920x1080 pairs (seeded S/T pool, true shift (-0.37,+0.61) px, every 8th with a defect), "
+            "default options (threshold 5, span 10, pyrLevels 3, winSize 30, pyrIterations 3, polyN 7, polySigma 1.5, flags 256)")
+# algorithmic HBM bytes per pair of the minimum-pass pipeline, SURVEY.md 8(d) / BASELINE.md section 2
+B_ALG = {"cfg2": 859248000.0, "cfg3": 5251873920.0, "cfg4": 1060800000.0}
 
 
 def measured_peaks():
@@ -69,30 +78,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                sm.append(float(f[0])); mx = float(f[1]); pw.append(float(f[2]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         # under load = samples in the top half of what we saw (idle samples at the edges are dropped)
-        if sm:
-            hi = [s for s in sm if s >= 0.5 * max(sm)]
-            med = float(np.median(hi))
-        else:
-            med = None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        med = float(np.median([s for s in sm if s >= 0.5 * max(sm)])) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def make_pool(n: int):
+def make_pool(n: int, w: int = W, h: int = H, seed0: int = 100):
     import tidalwave_b200 as tw
-    return tw.synth.pool_pairs(n, W, H, seed0=100)
+    return tw.synth.pool_pairs(n, w, h, seed0=seed0)
 
 
 def cpu_reference(pairs, n_pairs: int, workers: int):
@@ -104,15 +109,21 @@ def cpu_reference(pairs, n_pairs: int, workers: int):
         import cv2
         cv2.ipp.setUseIPP(False)
         cv2.setNumThreads(1)
-        impl = f"cv2 {cv2.__version__} calcOpticalFlowFarneback (the reference's third-party library, IPP off, 1 thread/pair) + sampling"
+        # what the reference itself executes on this path is this library call (src/opticalflow.cpp:83-85); its own code
+        # around it (sampling, src/consumer.cpp:60-77) is restated in NumPy
+        kind = "reference"
+        impl = (f"cv2 {cv2.__version__} calcOpticalFlowFarneback (the reference's third-party Farneback implementation -- OpenCV, newer "
+                "build than its 2.4.9 pin -- IPP off, 1 thread per pair) + the reference's sampling loop restated in NumPy")
 
         def one(i):
             a, b = pairs[i % len(pairs)]
             fl = cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 30, 3, 7, 1.5, 256)
             return sample_numpy(fl)[0]
     except Exception:
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
         O = RefOracle()
-        impl = "oracle/farneback_ref.c (scalar C port) + sampling"
+        kind = "port"
+        impl = "oracle/farneback_ref.c (scalar C port of the same algorithm, 1 thread per pair) + sampling"
 
         def one(i):
             a, b = pairs[i % len(pairs)]
@@ -122,7 +133,7 @@ def cpu_reference(pairs, n_pairs: int, workers: int):
     with ThreadPoolExecutor(workers) as ex:
         list(ex.map(one, range(n_pairs)))
     dt = time.perf_counter() - t0
-    return n_pairs / dt, "port", f"{n_pairs} pairs of the 1920x1080 pool, {workers} threads across pairs; {impl}"
+    return n_pairs / dt, kind, f"{n_pairs} pairs of the 1920x1080 pool, {workers} threads across pairs; {impl}"
 
 
 def run_reference(args, rank):
@@ -143,23 +154,107 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic 1920x1080 pairs, default options (threshold 5, span 10, pyrLevels 3, winSize 30, "
-                                   "polyN 7, flags 256)", "pairs_per_step": per_step},
+            "config": {"workload": WORKLOAD, "pairs_per_step": per_step, "where": "host CPU cores, no GPU"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+class Resident:
+    """A batch of pairs resident in one context's HBM + the timing helpers around tw_batch_run."""
+
+    def __init__(self, tw, lib, device, pairs, param, w, h):
+        self.tw, self.lib, self.w, self.h, self.B = tw, lib, w, h, len(pairs)
+        self.of = tw.OpticalFlow(device, w, h, self.B)
+        self.cp = param.c()
+        self.threshold, self.span = 5.0, 10
+        npx = w * h
+        self.pinned = []
+        for a, b in pairs:
+            pa = lib.tw_host_alloc(npx); pb = lib.tw_host_alloc(npx)
+            C.memmove(pa, a.ctypes.data, npx); C.memmove(pb, b.ctypes.data, npx)
+            self.pinned.append((pa, pb))
+        ex = (C.c_void_p * self.B)(*[p[0] for p in self.pinned])
+        tg = (C.c_void_p * self.B)(*[p[1] for p in self.pinned])
+        self.check(lib.tw_batch_upload(self.of.ctx, self.B, ex, tg, w, h, w), "upload")
+        self.check(lib.tw_sync(self.of.ctx), "sync")
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: rc={rc} {self.of.last_error()}")
+
+    def step(self):
+        self.check(self.lib.tw_l2_flush(self.of.ctx), "flush")
+        self.check(self.lib.tw_batch_run(self.of.ctx, self.B, self.w, self.h, C.byref(self.cp), self.threshold, self.span), "run")
+
+    def timed(self, steps, warmup, dist):
+        """-> device milliseconds of `steps` steps, max over ranks (barrier + stream sync on both sides)."""
+        for _ in range(warmup):
+            self.step()
+        self.check(self.lib.tw_sync(self.of.ctx), "sync")
+        dist.barrier()
+        self.check(self.lib.tw_timer_start(self.of.ctx), "timer")
+        for _ in range(steps):
+            self.step()
+        ms = C.c_float(0)
+        self.check(self.lib.tw_timer_stop(self.of.ctx, C.byref(ms)), "timer")  # records + synchronises the stream
+        dist.barrier()
+        return dist.reduce_max(float(ms.value))
+
+    def statuses(self):
+        cap = ((self.w + self.span - 1) // self.span) * ((self.h + self.span - 1) // self.span)
+        vec = (self.tw.tw_vector * (cap * self.B))()
+        res = (self.tw.tw_result * self.B)()
+        self.check(self.lib.tw_batch_fetch(self.of.ctx, self.B, vec, cap, res), "fetch")
+        return [res[i].status for i in range(self.B)]
+
+    def close(self):
+        self.of.close()
+        for pa, pb in self.pinned:
+            self.lib.tw_host_free(pa); self.lib.tw_host_free(pb)
+
+
+def run_pool(tw, lib, devices, B, cp, pinned, n_req, warm):
+    """n_req pairs cycled from the pinned host pool through ONE dispatcher (tw_pool_*) over `devices`; -> (seconds, vectors)."""
+    perr = C.create_string_buffer(256)
+    dv = (C.c_int * len(devices))(*devices)
+    pool = lib.tw_pool_create(dv, len(devices), W, H, B, C.byref(cp), 5.0, 10, 4096, perr, 256)
+    if not pool:
+        raise RuntimeError("tw_pool_create: " + perr.value.decode())
+    rvec = (tw.tw_vector * 4096)()
+    rres = tw.tw_result()
+    P = len(pinned)
+
+    def go(n):
+        ids = [lib.tw_pool_submit(pool, pinned[i % P][0], W, H, pinned[i % P][1], W, H) for i in range(n)]
+        nv = 0
+        for i in ids:
+            rc = lib.tw_pool_wait(pool, i, rvec, 4096, C.byref(rres))
+            if rc != 0:
+                raise RuntimeError(f"pool wait rc={rc} {rres.reason.decode()}")
+            nv += min(rres.n_vectors, 4096)
+        return nv
+    try:
+        go(warm)  # plans, buffers, graphs
+        t0 = time.perf_counter()
+        nv = go(n_req)
+        dt = time.perf_counter() - t0
+    finally:
+        lib.tw_pool_destroy(pool)
+    return dt, nv
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pool-consumers", type=int, default=2, help="e2e leg: consumer threads (contexts/streams) per GPU")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e, variants and configs legs (profilers)")
+    ap.add_argument("--pool-consumers", type=int, default=2, help="e2e leg: consumer threads (contexts) per GPU")
+    ap.add_argument("--e2e-pairs", type=int, default=10000, help="e2e leg: pairs per rank (BASELINE configs[4])")
     ap.add_argument("--arithmetic", default="default", choices=["default", "faithful"],
                     help="default = the library default (relaxed where validated: include/tidalwave_b200.h); faithful = the "
                          "oracle's operation order everywhere (bit-identical results)")
@@ -167,7 +262,8 @@ def main():
                     help="last iteration of the finest scale: 'sparse' = evaluated at the sampled positions only (what the dispatcher "
                          "does: the Response carries vectors, not the field; bit-identical vectors), 'dense' = full flow field")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,77 +274,35 @@ def main():
         return
 
     import tidalwave_b200 as tw
-    dist = tw.dist.Dist()  # nccl when launched by torch.distributed.run with N > 1; no-op at N = 1
+    dist = tw.dist.Dist()  # gloo barrier / max-reduce when launched by torch.distributed.run with N > 1; no-op at N = 1
     lib = tw.load()
     B = args.batch
     pairs = make_pool(B)  # every rank: same seeded pool, its own copy (weak scaling: B pairs per step per GPU)
     if args.arithmetic == "faithful":
         tw.set_default_arithmetic(False)  # contexts created from here on, the e2e pool's consumers included
-    of = tw.OpticalFlow(local_rank, W, H, B)
-    of.set_option("sparse_last", 1 if args.last == "sparse" else 0)
     os.environ["TW_SPARSE_LAST"] = "1" if args.last == "sparse" else "0"  # the e2e pool's consumers
     param = tw.OpticalFlowParameter()
+    R = Resident(tw, lib, local_rank, pairs, param, W, H)
+    of = R.of
+    of.set_option("sparse_last", 1 if args.last == "sparse" else 0)
     arithmetic = of.arithmetic_in_effect(param)
-    cp = param.c()
-    threshold, span = 5.0, 10
-
-    # pinned host copies of the pool
     npx = W * H
-    pinned = []
-    for a, b in pairs:
-        pa = lib.tw_host_alloc(npx); pb = lib.tw_host_alloc(npx)
-        C.memmove(pa, a.ctypes.data, npx); C.memmove(pb, b.ctypes.data, npx)
-        pinned.append((pa, pb))
-    ex = (C.c_void_p * B)(*[p[0] for p in pinned])
-    tg = (C.c_void_p * B)(*[p[1] for p in pinned])
-    cap = ((W + span - 1) // span) * ((H + span - 1) // span)
-    vec = (tw.tw_vector * (cap * B))()
-    res = (tw.tw_result * B)()
 
-    def check(rc, what):
-        if rc != 0:
-            raise RuntimeError(f"{what}: rc={rc} {of.last_error()}")
-
-    # ---- device-resident pass: inputs in HBM before the timed region ----
-    check(lib.tw_batch_upload(of.ctx, B, ex, tg, W, H, W), "upload")
-    check(lib.tw_sync(of.ctx), "sync")
-
-    def step():
-        check(lib.tw_l2_flush(of.ctx), "flush")
-        check(lib.tw_batch_run(of.ctx, B, W, H, C.byref(cp), threshold, span), "run")
-
-    for _ in range(args.warmup):
-        step()
-    check(lib.tw_sync(of.ctx), "sync")
-    # sanity: the warm-up results are real
-    check(lib.tw_batch_fetch(of.ctx, B, vec, cap, res), "fetch")
-    statuses = [res[i].status for i in range(B)]
-
-    barrier = dist.barrier
-
+    # ---- headline: device-resident pass ----
+    R.timed(0, args.warmup, dist)
+    statuses = R.statuses()  # sanity: the warm-up results are real
     l0 = of.launch_count()
     sampler = ClockSampler(local_rank)
-    barrier()
-    check(lib.tw_sync(of.ctx), "sync")
-    check(lib.tw_timer_start(of.ctx), "timer")
-    for _ in range(args.steps):
-        step()
-    ms = C.c_float(0)
-    check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")  # records + synchronises the stream
-    barrier()
+    elapsed_ms = R.timed(args.steps, 0, dist)
     clocks = sampler.stop()
     launches = of.launch_count() - l0
-    elapsed_ms = dist.reduce_max(float(ms.value))  # device time of the slowest rank
     value = tw.dist.whole_job_throughput(B * args.steps, world, elapsed_ms * 1e-3)
 
-    # ---- per-kernel-family pass: the same K steps again with a CUDA event pair around every launch (the graph replay
-    # above has no per-kernel events; with profiling on the library issues the identical launch sequence eagerly) ----
+    # ---- per-kernel-family pass: the same steps again with a CUDA event pair around every launch (the graph replay above
+    # has no per-kernel events; with profiling on the library issues the identical launch sequence eagerly) ----
+    psteps = min(args.steps, 100)
     of.profile(True)
-    check(lib.tw_timer_start(of.ctx), "timer")
-    for _ in range(args.steps):
-        step()
-    check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")
-    prof_ms = float(ms.value)
+    prof_ms = R.timed(psteps, 0, dist)
     prof = of.profile_read()
     of.profile(False)
 
@@ -264,7 +318,7 @@ def main():
     traffic, traffic_src = None, None
     try:
         import glob
-        for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_traffic.json")), reverse=True):
             tj = json.load(open(tf))
             if tj.get("batch") == B and tj.get("arithmetic", "faithful") == arithmetic and top in tj:
                 traffic = tj[top]["dram_bytes_per_launch"]
@@ -272,89 +326,104 @@ def main():
                 break
     except Exception:
         pass
+    step_rate = B * args.steps / (elapsed_ms * 1e-3)  # this rank's pairs/s (= value / world)
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "timed": "per-launch CUDA events on the library's stream over a second pass of the same %d steps (eager launches; the "
-                         "headline pass replays a CUDA graph): %.3f ms/step" % (args.steps, prof_ms / args.steps), "avg_launch_ms": tv["ms"] / tv["launches"],
+                "timed": "per-launch CUDA events on the library's stream over a second pass of %d steps (eager launches; the headline "
+                         "pass replays a CUDA graph): %.3f ms/step" % (psteps, prof_ms / psteps), "avg_launch_ms": tv["ms"] / tv["launches"],
                 "alg_bytes_per_launch": tv["alg_bytes"] / tv["launches"], "share_of_step": tv["ms"] / kernel_ms_total,
-                "pipeline": {"alg_bytes_per_pair": alg_total / (B * args.steps), "achieved": alg_total / (elapsed_ms * 1e-3) / 1e9,
-                             "frac": alg_total / (elapsed_ms * 1e-3) / 1e9 / peak,
-                             "note": "whole step (all kernels + launch gaps + the L2 flush) of the headline pass vs the HBM peak"},
-                "families": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                                 "GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in fams.items()}}
+                "pipeline": {"alg_bytes_per_pair": alg_total / (B * psteps),
+                             "alg_bytes_per_pair_survey": B_ALG["cfg2"],
+                             "achieved": step_rate * alg_total / (B * psteps) / 1e9,
+                             "frac": step_rate * alg_total / (B * psteps) / 1e9 / peak,
+                             "frac_vs_survey_bytes": step_rate * B_ALG["cfg2"] / 1e9 / peak,
+                             "note": "whole step (all kernels + launch gaps + the L2 flush) of the headline pass vs the HBM peak; "
+                                     "alg_bytes_per_pair is what THIS step moves by the formula of SURVEY 8(d) (the sparse last iteration "
+                                     "writes no finest-scale flow plane and reads M once: 859.2 -> 842.7 MB); frac_vs_survey_bytes charges the "
+                                     "full 859.2 MB regardless"},
+                "families": {k: {"ms_per_step": v["ms"] / psteps, "launches_per_step": v["launches"] / psteps,
+                                 "GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None,
+                                 "frac": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak) if v["ms"] > 0 else None} for k, v in fams.items()},
+                "families_note": "level_image is charged what the fused kernel moves: the u8 source ONCE for all four levels + the level "
+                                 "images written (SURVEY's formula charges the source once per level)"}
 
-    # ---- e2e: dispatcher API, pinned host images in, result structs out ----
-    e2e = None
+    e2e = variants = configs = e2e_inprocess = None
     if not args.no_e2e:
-        nc = max(1, args.pool_consumers)
-        n_req = max(B * nc * 4, 2048 // B * B)  # ~1 s of work: short runs are dominated by pool start-up jitter
-        perr = C.create_string_buffer(256)
-        dv = (C.c_int * nc)(*([local_rank] * nc))  # several consumers per GPU: one uploads while another computes
-        pool = lib.tw_pool_create(dv, nc, W, H, B, C.byref(cp), threshold, span, 4096, perr, 256)
-        if not pool:
-            raise RuntimeError("tw_pool_create: " + perr.value.decode())
-        rvec = (tw.tw_vector * 4096)()
-        rres = tw.tw_result()
-
-        def run_pool(n):
-            ids = [lib.tw_pool_submit(pool, pinned[i % B][0], W, H, pinned[i % B][1], W, H) for i in range(n)]
-            nv = 0
-            for i in ids:
-                rc = lib.tw_pool_wait(pool, i, rvec, 4096, C.byref(rres))
-                if rc != 0:
-                    raise RuntimeError(f"pool wait rc={rc} {rres.reason.decode()}")
-                nv += min(rres.n_vectors, 4096)
-            return nv
-
-        run_pool(2 * B)  # warm-up (plans, buffers)
-        barrier()
-        t0 = time.perf_counter()
-        nv = run_pool(n_req)
-        dt = dist.reduce_max(time.perf_counter() - t0)
-        lib.tw_pool_destroy(pool)
-        e2e = {"value": world * n_req / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * npx * B,
-               "d2h_bytes_per_step": int(4 * B + 24 * nv * B / n_req), "pairs": n_req,
-               "api": "tw_pool_submit/tw_pool_wait, %d consumers per GPU, batch %d, pinned host images" % (nc, B)}
-
-    # ---- the other arithmetic, reported beside the headline ----
-    variants = None
-    if not args.no_e2e:
-        other = 0 if arithmetic == "relaxed" else 1
-        of.set_option("arithmetic", other)
-        other_name = of.arithmetic_in_effect(param)
-        for _ in range(3):
-            step()
-        check(lib.tw_sync(of.ctx), "sync")
-        barrier()
-        check(lib.tw_timer_start(of.ctx), "timer")
-        nv = max(3, args.steps // 2)
-        for _ in range(nv):
-            step()
-        check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")
-        o_ms = dist.reduce_max(float(ms.value))
-        of.set_option("arithmetic", 1 - other)
+        # ---- the other forms of the same step, beside the headline ----
+        nv = max(20, args.steps // 4)
+        variants = {}
         notes = {"faithful": "tw_set_option(arithmetic, 0): every kernel in the oracle's operation order, results bit-identical to "
-                             "oracle/farneback_ref.c and <= 1.2e-7 px from cv2 on this workload",
+                             "oracle/farneback_ref.c",
                  "relaxed": "tw_set_option(arithmetic, 1): direct-form fmaf window taps + mixed double/float poly-exp pass; <= 1.5e-4 px from "
-                            "the faithful oracle at 1920x1080, status / vectors identical"}
-        variants = {other_name: {"value": tw.dist.whole_job_throughput(B * nv, world, o_ms * 1e-3), "unit": UNIT,
-                                 "ms_per_step": o_ms / nv, "note": notes[other_name]}}
-        # the other form of the last iteration, same arithmetic as the headline
-        of.set_option("sparse_last", 0 if args.last == "sparse" else 1)
-        for _ in range(3):
-            step()
-        check(lib.tw_sync(of.ctx), "sync")
-        barrier()
-        check(lib.tw_timer_start(of.ctx), "timer")
-        for _ in range(nv):
-            step()
-        check(lib.tw_timer_stop(of.ctx, C.byref(ms)), "timer")
-        l_ms = dist.reduce_max(float(ms.value))
+                            "the faithful oracle at 1920x1080, status / vectors identical",
+                 "sparse": "last iteration of the finest scale at the sampled positions only (the dispatcher's form; vectors bit-identical)",
+                 "dense": "the whole flow field is produced (tw_flow / tw_batch_flow callers)"}
+        for ar in ("relaxed", "faithful"):
+            for la in ("sparse", "dense"):
+                if ar == arithmetic and la == args.last:
+                    continue
+                of.set_option("arithmetic", 1 if ar == "relaxed" else 0)
+                of.set_option("sparse_last", 1 if la == "sparse" else 0)
+                ms = R.timed(nv, 3, dist)
+                variants[f"{ar}_{la}"] = {"value": tw.dist.whole_job_throughput(B * nv, world, ms * 1e-3), "unit": UNIT, "ms_per_step": ms / nv,
+                                          "note": notes[ar] + "; " + notes[la]}
+        of.set_option("arithmetic", 1 if arithmetic == "relaxed" else 0)
         of.set_option("sparse_last", 1 if args.last == "sparse" else 0)
-        lname = "dense_last_iteration" if args.last == "sparse" else "sparse_last_iteration"
-        variants[lname] = {"value": tw.dist.whole_job_throughput(B * nv, world, l_ms * 1e-3), "unit": UNIT, "ms_per_step": l_ms / nv,
-                           "note": ("the whole flow field is produced (tw_flow / tw_batch_flow callers); identical vectors and status"
-                                    if args.last == "sparse" else "blur + solve of the last iteration at the sampled positions only")}
+    R.close()
+
+    if not args.no_e2e:
+        # ---- e2e = BASELINE configs[4]: 10,000 pairs from 64 distinct pinned host pairs through the dispatcher ----
+        POOL = 64
+        pool_pairs = pairs + make_pool(POOL - B, seed0=100 + B) if POOL > B else pairs[:POOL]
+        pinned = []
+        for a, b in pool_pairs:
+            pa = lib.tw_host_alloc(npx); pb = lib.tw_host_alloc(npx)
+            C.memmove(pa, a.ctypes.data, npx); C.memmove(pb, b.ctypes.data, npx)
+            pinned.append((pa, pb))
+        cp = param.c()
+        nc = max(1, args.pool_consumers)
+        n_req = max(args.e2e_pairs // B * B, B * nc * 4)
+        dist.barrier()
+        dt, nvec = run_pool(tw, lib, [local_rank] * nc, B, cp, pinned, n_req, 2 * B * nc)
+        dt = dist.reduce_max(dt)
+        e2e = {"value": world * n_req / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * npx * B,
+               "d2h_bytes_per_step": int(4 * B + 24 * nvec * B / n_req), "pairs": n_req * world, "seconds": dt,
+               "api": "tw_pool_submit/tw_pool_wait (configs[4]: %d pairs per GPU cycled from %d distinct pinned host pairs), %d consumer(s) per "
+                      "GPU, batch %d" % (n_req, POOL, nc, B)}
+        dist.barrier()
+        if world > 1:
+            # ONE in-process dispatcher over all N GPUs (rank 0), the reference's Manager + Consumers shape; other ranks idle
+            if rank == 0:
+                ndev = min(world, lib.tw_device_count())
+                dti, _ = run_pool(tw, lib, [d for d in range(ndev) for _ in range(nc)], B, cp, pinned, n_req * ndev, 2 * B * nc * ndev)
+                e2e_inprocess = {"value": n_req * ndev / dti, "unit": UNIT, "gpus": ndev, "pairs": n_req * ndev, "seconds": dti,
+                                 "api": "one tw_pool in ONE process, %d consumer thread(s) on each of %d GPUs" % (nc, ndev)}
+            dist.barrier()
+        for pa, pb in pinned:
+            lib.tw_host_free(pa); lib.tw_host_free(pb)
+
+        # ---- BASELINE configs[2] and configs[3], device-resident, each against its own roofline (rank-local; N = 1 only) ----
+        if world == 1:
+            configs = {}
+            for key, (w_, h_, b_, kw, gen) in {
+                    "cfg3": (3840, 2160, 4, dict(pyrLevels=5, pyrIterations=5), [("T", 4), ("S", 5), ("T", 14), ("S", 15)]),
+                    "cfg4": (1280, 2000, 8, dict(polyN=5, polySigma=1.1, winSize=15, flags=0), [("S", 3), ("T", 6)] * 4)}.items():
+                prs = [tw.synth.make_pair(k, w_, h_, s, False) for k, s in gen][:b_]
+                p_ = tw.OpticalFlowParameter(**kw)
+                Rc = Resident(tw, lib, local_rank, prs, p_, w_, h_)
+                ns = 20
+                ms = Rc.timed(ns, 3, dist)
+                v_ = b_ * ns / (ms * 1e-3)
+                Rc.of.profile(True)
+                Rc.timed(5, 0, dist)
+                pf = {k: v for k, v in Rc.of.profile_read().items() if v["launches"] > 0}
+                Rc.of.profile(False)
+                configs[key] = {"workload": "%dx%d, %s, batch %d" % (w_, h_, ", ".join(f"{k}={v}" for k, v in kw.items()), b_),
+                                "value": v_, "unit": UNIT, "ms_per_pair": ms / ns / b_, "arithmetic": Rc.of.arithmetic_in_effect(p_),
+                                "alg_bytes_per_pair": B_ALG[key], "roofline_pairs_per_s": peak * 1e9 / B_ALG[key],
+                                "frac": v_ * B_ALG[key] / 1e9 / peak,
+                                "families_ms_per_pair": {k: v["ms"] / 5 / b_ for k, v in pf.items()}}
+                Rc.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -367,25 +436,23 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[1]/[4]: batch of %d synthetic 1920x1080 pairs per step per GPU (seeded S/T pool, true shift "
-                                       "(-0.37,+0.61) px, every 8th with a defect), default options (threshold 5, span 10, pyrLevels 3, "
-                                       "winSize 30, pyrIterations 3, polyN 7, polySigma 1.5, flags 256)" % B,
-                           "batch": B,
+                "config": {"workload": WORKLOAD, "pairs_per_step": B, "batch": B,
                            "arithmetic": ("relaxed (library default for this option family): direct-form fmaf Gaussian window taps + mixed "
                                           "double/float horizontal poly-exp pass; measured <= 1.5e-4 px from the faithful oracle at "
-                                          "1920x1080 (bar 1e-2), status and vectors identical; tests/test_gpu_relaxed.py")
+                                          "1920x1080 (bar 1e-2), status and vectors identical; tests/test_gpu_relaxed.py, "
+                                          "tests/test_gpu_configs_fullsize.py; variants.faithful_* time the oracle's own arithmetic")
                            if arithmetic == "relaxed" else "faithful: the oracle's operation order, bit-identical results",
                            "last_iteration": ("sparse: the finest scale's last blur + solve runs only at the positions the reference samples "
                                               "(src/consumer.cpp:60-77), as in the dispatcher -- the Response carries vectors and status, never "
                                               "the field; vectors bit-identical to the dense path (tests/test_gpu_sparse_last.py); the dense form "
-                                              "is timed in variants.dense_last_iteration") if args.last == "sparse" else "dense: full flow field",
+                                              "is timed in variants.*_dense") if args.last == "sparse" else "dense: full flow field",
                            "launch": "one CUDA graph replay per step (%d kernel nodes)" % (launches // max(args.steps, 1)),
                            "parallelism": "independent pairs per GPU, no collective",
-                           "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "gpu_launches": int(launches), "clocks": clocks,
-                "statuses": statuses}
+                           "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2",
+                           "timed_region_s": elapsed_ms * 1e-3},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_inprocess": e2e_inprocess, "variants": variants, "configs": configs,
+                "gpu_launches": int(launches), "clocks": clocks, "statuses": statuses}
         print(json.dumps(line), flush=True)
-    of.close()
     dist.close()
 
 

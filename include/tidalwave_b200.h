@@ -148,6 +148,9 @@ const char *tw_last_error(tw_ctx *ctx);
  *   "gauss_fma"  = 1: symmetric fmaf in the Gaussian window tap sums on top of the faithful arithmetic (oracle relax bit 0).
  *   "update_fma" = 1: fmaf chains in the update matrices on top of "arithmetic" = 1 (oracle relax bit 6; studied, rejected
  *                     as a default: 0.157 px on the reference's scenario1 fixture).
+ *   "window_tiles" = 0 / 1: the Gaussian window iterations of radius 15 run the persistent warp-specialised strip kernel
+ *                     (tw_window.cu: TMA-fed rings, register-resident column walkers) / the tile-per-CTA kernel.  Same
+ *                     arithmetic, bit-identical results; TW_WINDOW=strip|tiles in the environment sets the default.
  *   "gauss_scalar", "level_generic", "level_unfused", "tight_pitch": alternative code paths kept for the parity tests. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);
 /* Process-wide default of "arithmetic" for contexts created afterwards (the dispatcher's consumers included). */
@@ -182,7 +185,10 @@ int tw_debug_keep_levels(tw_ctx *ctx, int on); /* keep every scale's I/R/M (sepa
 /* ---- dispatcher: Manager + Consumer pool (src/manager.cpp:40-98, src/consumer.cpp:12-94) ----
  * One host thread per entry of devices[] (consumer i binds GPU devices[i]), all blocking on one shared
  * request queue; options are fixed per pool (src/manager.cpp:72-73).  Images are caller-owned and must
- * stay valid until the result for that id has been taken.  No CPU fallback worker. */
+ * stay valid until the result for that id has been taken.  No CPU fallback worker.
+ * vector_cap > 0: at most that many vectors are kept per request (tw_result.n_vectors still holds the full count);
+ * vector_cap == 0: all of them, whatever the image size (capacity = the request's own sampling grid).
+ * max_w / max_h > 0 bound the image size a consumer accepts (larger requests answer TW_BAD_PARAMETER); 0 = no bound. */
 tw_pool *tw_pool_create(const int *devices, int n_devices, int max_w, int max_h, int batch,
                         const tw_flow_param *param, double threshold, int span, int vector_cap,
                         char *err, int errlen);

@@ -301,3 +301,60 @@ def test_pool_all_devices(tw, golden):
     pool.stop(); pool.close()
     assert rep == {"request": 8 * n, "data": 8 * n, "error": 0}
     assert all(r["status"] == "SUSPICIOUS" and len(r["vector"]) == 24 for r in out)
+
+
+def test_pool_mixed_sizes_return_every_vector(tw):
+    """Screenshot directories mix page sizes (index.js:33-73 feeds whatever the glob finds): a small OK pair followed by a larger
+    SUSPICIOUS pair through one dispatcher with vector_cap = 0 must return EVERY vector of the larger pair, as the reference
+    does (src/consumer.cpp:60-76) -- the capacity follows each request, not the first one."""
+    small = tw.synth.make_pair("T", 200, 120, 3)
+    big = tw.synth.make_pair("S", 960, 540, 100, defect=True)
+    o = tw.OpticalFlow(0, 0, 0, 1)
+    want_small, want_big = o.calculate(*small, threshold=0.3), o.calculate(*big, threshold=0.3)
+    o.close()
+    assert want_big["status"] == "SUSPICIOUS" and len(want_big["vector"]) > 24 * 12  # more than the small pair's whole grid
+    pool = tw.Pool([0, 0], batch=2, threshold=0.3)  # max_w = max_h = vector_cap = 0
+    ids = [pool.request(*small), pool.request(*big), pool.request(*small), pool.request(*big)]
+    out = [pool.wait(i) for i in ids]
+    pool.stop(); pool.close()
+    for got, want in zip(out, (want_small, want_big, want_small, want_big)):
+        assert got["status"] == want["status"] and got["vector"] == want["vector"] and got["n_vectors"] == len(got["vector"])
+
+
+def test_context_size_bound_is_enforced(tw):
+    """tw_create's max_w / max_h bound the images a context accepts; 0 = no bound."""
+    a, b = tw.synth.make_pair("T", 200, 120, 3)
+    o = tw.OpticalFlow(0, 160, 120, 1)
+    r = o.calculate(a, b)
+    assert r["status"] == "ERROR" and r["code"] == 1
+    o.close()
+    o = tw.OpticalFlow(0, 200, 120, 1)
+    assert o.calculate(a, b)["status"] != "ERROR"
+    o.close()
+
+
+@pytest.mark.parametrize("size,seed,batch", [((1920, 1080), 100, 2), ((500, 333), 7, 3), ((97, 61), 9, 1), ((960, 540), 11, 1)])
+def test_strip_window_kernel_bit_identical(tw, oracle, size, seed, batch):
+    """The persistent strip window kernel ("window_tiles" = 0) and the tile kernel run the same arithmetic: bit-identical to
+    each other and to the oracle in both arithmetics, on ragged strip / group geometry (w % 96 != 0, h % 8 != 0), with a defect
+    (motion boundary: the global-memory gather path of the epilogue), on the last and the non-last iterations, batched."""
+    w, h = size
+    a, b = tw.synth.make_pair("S", w, h, seed, defect=True)
+    pairs = [(a, b)] + [tw.synth.make_pair("T", w, h, seed + 1 + i) for i in range(batch - 1)]
+    o = tw.OpticalFlow(0, w, h, batch)
+    ref = {}
+    for bits in (0, 144):
+        oracle.set_relax(bits)
+        ref[bits] = oracle.farneback(a, b, FlowParam())
+    oracle.set_relax(0)
+    for tiles in (1, 0):
+        o.set_option("window_tiles", tiles)
+        for arith, bits in ((0, 0), (1, 144)):
+            o.set_option("arithmetic", arith)
+            for _ in range(2):  # eager, then the captured graph
+                res = o.calculate_batch(pairs, threshold=0.5)
+                fx, fy = o.batch_flow(0, w, h)
+                assert np.array_equal(fx, ref[bits][..., 0]) and np.array_equal(fy, ref[bits][..., 1]), (tiles, arith)
+            status, vec = oracle.sample(ref[bits], 10, 0.5)
+            assert res[0]["status"] == status and _vec_pos(res[0]) == [(v[0], v[1]) for v in vec]
+    o.close()

@@ -281,7 +281,9 @@ class Pool:
     """Manager + Consumer pool (src/manager.cpp:40-98): one consumer thread per entry of ``devices``."""
 
     def __init__(self, devices, param: OpticalFlowParameter = OpticalFlowParameter(), threshold: float = 5.0, span: int = 10,
-                 max_w: int = 1920, max_h: int = 1080, batch: int = 1, vector_cap: int = 4096):
+                 max_w: int = 0, max_h: int = 0, batch: int = 1, vector_cap: int = 0):
+        """max_w / max_h = 0: no bound on the image size; vector_cap = 0: every vector of every request is returned (the capacity
+        follows each request's own sampling grid), > 0: at most that many (``n_vectors`` still holds the full count)."""
         self.lib = load()
         self.span, self.threshold, self.cap = span, threshold, vector_cap
         err = C.create_string_buffer(256)
@@ -306,13 +308,18 @@ class Pool:
         return rid
 
     def wait(self, rid: int) -> dict | None:
-        vec = (tw_vector * max(self.cap, 1))()
+        cap = self.cap
+        if cap <= 0:  # all vectors: the request's own sampling grid (src/consumer.cpp:60-76)
+            a = self._keep.get(rid, (None, None))[0]
+            eh, ew = a.shape if a is not None else (0, 0)
+            cap = max(1, ((ew + self.span - 1) // self.span) * ((eh + self.span - 1) // self.span))
+        vec = (tw_vector * cap)()
         res = tw_result()
-        rc = self.lib.tw_pool_wait(self.pool, rid, vec, self.cap, C.byref(res))
+        rc = self.lib.tw_pool_wait(self.pool, rid, vec, cap, C.byref(res))
         self._keep.pop(rid, None)
         if rc < 0:
             return None
-        return _response(res, vec, min(res.n_vectors, self.cap), self.span, self.threshold)
+        return _response(res, vec, min(res.n_vectors, cap), self.span, self.threshold)
 
     def report(self) -> dict:
         a = C.c_int(); b = C.c_int(); c = C.c_int()

@@ -4,6 +4,8 @@
 #include "../../include/tidalwave_b200.h"
 #include "tw_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: one range per launch, named after the kernel family (tracing)
+
 #include <atomic>
 #include <cfloat>
 #include <cmath>
@@ -34,6 +36,7 @@ struct Scale {
     std::vector<float> host_taps;
     // buffers (alias the shared work buffers unless keep_levels)
     float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr, *flow = nullptr;
+    StripMaps maps[2] = {}; // tensor maps of the strip window kernel reading M0 / M1 (and R) at this scale
 };
 
 struct Plan {
@@ -63,14 +66,15 @@ struct tw_ctx {
     bool last_sparse = false; // the previous run left no dense field
     int opt_update_fma = 0; // studied opt-in (oracle relax bit 6), never part of "arithmetic" = 1
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
+    int opt_window_tiles = 1; // 1: the tile-per-CTA window kernel (gauss_iter2_kernel); 0: the persistent strip kernel (tw_window.cu)
     int opt_arith = 1;  // 0 = faithful (App. A operation order), 1 = relaxed where validated (relaxed_in_effect)
     int opt_graph = 1;  // replay the launch sequence of a batch from a captured CUDA graph
     // CUDA graph of the launch sequence (enqueue) for one (plan, n, threshold, span, options) key
     struct GraphKey {
-        unsigned long long plan_gen = 0; int n = 0; double thr = 0; int span = 0; int opts = 0; const void *vectors = nullptr;
+        unsigned long long plan_gen = 0; int n = 0; double thr = 0; int span = 0; int opts = 0; const void *vectors = nullptr; int dev_cap = 0;
         bool operator==(const GraphKey &o) const
         {
-            return plan_gen == o.plan_gen && n == o.n && thr == o.thr && span == o.span && opts == o.opts && vectors == o.vectors;
+            return plan_gen == o.plan_gen && n == o.n && thr == o.thr && span == o.span && opts == o.opts && vectors == o.vectors && dev_cap == o.dev_cap;
         }
     };
     GraphKey graph_key, seen_key;
@@ -109,6 +113,7 @@ bool set_err(tw_ctx *c, const char *what, cudaError_t e)
     char buf[256];
     snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
     c->err = buf;
+    cudaGetLastError(); // clear the runtime's last-error slot: the next request's first launch must not inherit this failure
     return false;
 }
 
@@ -408,6 +413,11 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
         } else {
             s.R = R; s.M0 = M0; s.M1 = M1;
         }
+        s.maps[0].valid = s.maps[1].valid = 0;
+        if ((p.flags & 256) && pl.win.m == 15) { // no tensor maps (old driver?): the tile kernel runs instead
+            make_strip_maps(s.M0, s.R, s.d, B, &s.maps[0]);
+            make_strip_maps(s.M1, s.R, s.d, B, &s.maps[1]);
+        }
     }
     // the default pyramid (full resolution + exact 2x / 4x / 8x with 3 / 9 / 19-tap pre-blurs) takes the fused level kernel
     // (the FINEST four scales; deeper pyramids keep their coarser scales on the per-level kernels)
@@ -432,6 +442,7 @@ struct LaunchScope {
     tw_ctx *ctx; int fam; cudaEvent_t a = nullptr, b = nullptr;
     LaunchScope(tw_ctx *c, int f, double bytes) : ctx(c), fam(f)
     {
+        nvtxRangePushA(kFamilyNames[f]);
         ctx->launches++;
         if (ctx->profiling) {
             a = get_event(ctx); b = get_event(ctx);
@@ -443,6 +454,7 @@ struct LaunchScope {
     ~LaunchScope()
     {
         if (ctx->profiling) { cudaEventRecord(b, ctx->stream); ctx->recs.push_back({fam, a, b}); }
+        nvtxRangePop();
     }
 };
 
@@ -517,8 +529,9 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         double bytes = 0;
         for (int i = 0; i < 4; i++) {
             dst[i] = pl.scales[fbase + i].I; dd[i] = pl.scales[fbase + i].d;
-            bytes += n * (2 * P0 + 8.0 * dd[i].w * dd[i].h);
+            bytes += n * 8.0 * dd[i].w * dd[i].h;
         }
+        bytes += n * 2 * P0; // what this kernel moves: the u8 source ONCE for all four levels (SURVEY 8(d) charges it once per level)
         LAUNCH(F_LEVEL, bytes, launch_level_fused(ctx->stream, pl.src, W, H, pl.spitch, dst, dd, pl.scales[fbase].host_taps.data(),
                                                    pl.scales[fbase + 1].host_taps.data(), pl.scales[fbase + 2].host_taps.data(),
                                                    pl.scales[fbase + 3].host_taps.data(), 2 * n));
@@ -567,6 +580,8 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             if (ia.span > 0 && sparse_in_effect(ctx, span)) {
                 // classification only: blur + solve at the sampled positions (one pass over M, no flow plane written)
                 LAUNCH(F_GLAST, n * 20.0 * Pl, launch_gauss_last_sparse(ctx->stream, ia, pl.win));
+            } else if ((p.flags & 256) && !ctx->opt_window_tiles && gauss_strip_ok(ia, pl.win) && s.maps[Min == s.M1 ? 1 : 0].valid) {
+                LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_strip(ctx->stream, ia, pl.win, s.maps[Min == s.M1 ? 1 : 0]));
             } else if (p.flags & 256) {
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_iter(ctx->stream, ia, pl.win));
             } else {
@@ -603,8 +618,8 @@ bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
     if (!ctx->opt_graph || ctx->profiling) return enqueue(ctx, n, threshold, span);
     tw_ctx::GraphKey key;
     key.plan_gen = ctx->plan_gen; key.n = n; key.thr = threshold; key.span = span;
-    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5 | ctx->opt_sparse_last << 6;
-    key.vectors = ctx->d_vectors;
+    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5 | ctx->opt_sparse_last << 6 | ctx->opt_window_tiles << 7;
+    key.vectors = ctx->d_vectors; key.dev_cap = ctx->dev_cap; // the captured sample kernel bakes both in
     if (ctx->graph_exec && key == ctx->graph_key) {
         cudaError_t e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
         if (e != cudaSuccess) { set_err(ctx, "cudaGraphLaunch", e); return false; }
@@ -614,7 +629,7 @@ bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
     if (!(key == ctx->seen_key)) { // first run of this key: eager
         if (!enqueue(ctx, n, threshold, span)) return false;
         ctx->seen_key = key;
-        ctx->seen_key.vectors = ctx->d_vectors; // enqueue may have (re)allocated the result buffer
+        ctx->seen_key.vectors = ctx->d_vectors; ctx->seen_key.dev_cap = ctx->dev_cap; // enqueue may have (re)allocated the result buffer
         return true;
     }
     // second run: capture, instantiate, launch
@@ -715,6 +730,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
     ctx->opt_arith = default_arith();
     if (const char *g = getenv("TW_GRAPH")) ctx->opt_graph = atoi(g) ? 1 : 0; // TW_GRAPH=0: eager launches (profilers)
+    if (const char *g = getenv("TW_WINDOW")) ctx->opt_window_tiles = strcmp(g, "strip") ? 1 : 0; // TW_WINDOW=strip|tiles
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
     cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
     if ((e = cudaMalloc(&ctx->d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
@@ -772,6 +788,7 @@ static int upload_impl(tw_ctx *ctx, int n, const uint8_t *const *expect, const u
 {
     if (!ctx) return TW_BAD_PARAMETER;
     if (n < 1 || n > ctx->max_batch || w < 1 || h < 1 || stride < w) { ctx->err = "bad batch/size"; return TW_BAD_PARAMETER; }
+    if ((ctx->max_w > 0 && w > ctx->max_w) || (ctx->max_h > 0 && h > ctx->max_h)) { ctx->err = "image larger than the context's max_w x max_h"; return TW_BAD_PARAMETER; }
     cudaSetDevice(ctx->device);
     tw_flow_param p;
     if (param) p = *param; else if (ctx->plan.valid) p = ctx->plan.p; else tw_default_param(&p);
@@ -1062,6 +1079,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "sparse_last")) { ctx->opt_sparse_last = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "update_fma")) { ctx->opt_update_fma = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }

@@ -7,6 +7,7 @@
 // The algorithm restated here is OpenCV's calcOpticalFlowFarneback -- the single library call at
 // /root/reference/src/opticalflow.cpp:83-85 -- and the sampling loop of /root/reference/src/consumer.cpp:60-77.
 #include "tw_kernels.cuh"
+#include "tw_device.cuh"
 
 namespace tw {
 
@@ -19,8 +20,6 @@ static int current_device()
     cudaGetDevice(&d);
     return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // base + stride * row as ONE instruction (IMAD.WIDE.U32).  nvcc otherwise strength-reduces the unrolled row
 // addresses into chains of 64-bit adds + LEA pairs: 4 integer instructions per load in kernels whose inner loops
@@ -942,32 +941,6 @@ cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const Level
 // ------------------------------------------------------------------------------------------------
 // A.4  update matrices for one pixel.  All float, no FMA.  R0/R1 point at channel 0 of the pair's planes.
 // ------------------------------------------------------------------------------------------------
-// border damping {0.14, 0.14, 0.4472, 0.4472, 0.4472} indexed by the distance to the edge (App. A.4)
-__device__ __forceinline__ float border_tab(int i) { return i < 2 ? 0.14f : 0.4472f; }
-
-// ------------------------------------------------------------------------------------------------
-// R and M are ROW-INTERLEAVED planar (5*plane floats per image / pair): the five channels of image row y are the
-// five consecutive pitch-sized rows (y*5 + c).  With the compile-time pitch every channel, every bilinear neighbour
-// and every row of a register-blocked column is ONE base register + an immediate offset.
-//   R row group: [dy | dx | yy | xx | xy]                     each `pitch` floats
-//   M row group: [(G11,G12) float2 x pitch | (G22,h1) float2 x pitch | h2 float x pitch]   = 5*pitch floats
-// The packed f32x2 window kernel loads both channels of an M pair with one 8-byte load; writers store float2.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_M(float *__restrict__ Mb, int pitch, int y, int x, const float m[5])
-{
-    float *row = Mb + (size_t)y * 5 * pitch;
-    *reinterpret_cast<float2 *>(row + 2 * x) = make_float2(m[0], m[1]);
-    *reinterpret_cast<float2 *>(row + 2 * pitch + 2 * x) = make_float2(m[2], m[3]);
-    row[4 * pitch + x] = m[4];
-}
-// channel c of M as a strided scalar view: element (y, x) is base[(size_t)y * 5 * pitch + x * stride]
-__device__ __forceinline__ const float *M_channel(const float *Mb, int pitch, int c, int &stride)
-{
-    if (c < 4) { stride = 2; return Mb + (c >> 1) * 2 * pitch + (c & 1); }
-    stride = 1;
-    return Mb + 4 * pitch;
-}
-
 // The epilogues are latency-bound, so the 25 loads of a pixel are issued first (upd_load) for several pixels
 // and consumed afterwards (upd_compute).
 struct UpdLoad {
@@ -998,59 +971,6 @@ __device__ __forceinline__ void upd_load(const float *__restrict__ R0, const flo
     }
 }
 
-// UF = validated relaxation (oracle relax bit 6): fmaf chains in the bilinear blend, the flow terms and the outer
-// products (same association order as App. A.4); UF = false keeps the oracle's mul / add sequence (-fmad=false TU).
-// pt / pb = R1 at rows y1 / y1+1, columns (x1, x1+1); q = R0 at (x, y).
-template <bool UF, bool BORDER = true>
-__device__ __forceinline__ void upd_core(const float q[5], const float pt[5][2], const float pb[5][2], bool inside, float fx, float fy,
-                                         int w, int h, int x, int y, float dx, float dy, float m[5])
-{
-    float r[5];
-    if (inside) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            if (UF) r[c] = fmaf(a11, pb[c][1], fmaf(a10, pb[c][0], fmaf(a01, pt[c][1], a00 * pt[c][0])));
-            else r[c] = a00 * pt[c][0] + a01 * pt[c][1] + a10 * pb[c][0] + a11 * pb[c][1];
-        }
-        r[2] = (q[2] + r[2]) * 0.5f;
-        r[3] = (q[3] + r[3]) * 0.5f;
-        r[4] = (q[4] + r[4]) * 0.25f;
-    } else {
-        r[0] = r[1] = 0.f;
-        r[2] = q[2];
-        r[3] = q[3];
-        r[4] = q[4] * 0.5f;
-    }
-    float r2 = (q[0] - r[0]) * 0.5f, r3 = (q[1] - r[1]) * 0.5f, r4 = r[2], r5 = r[3], r6 = r[4];
-    if (UF) {
-        r2 = fmaf(r4, dy, fmaf(r6, dx, r2));
-        r3 = fmaf(r6, dy, fmaf(r5, dx, r3));
-    } else {
-        r2 = r2 + (r4 * dy + r6 * dx);
-        r3 = r3 + (r6 * dy + r5 * dx);
-    }
-    if (BORDER && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
-        float sc = (x < 5 ? border_tab(x) : 1.f) * (x >= w - 5 ? border_tab(w - x - 1) : 1.f) * (y < 5 ? border_tab(y) : 1.f) *
-                   (y >= h - 5 ? border_tab(h - y - 1) : 1.f);
-        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-    }
-    if (UF) {
-        const float r66 = r6 * r6;
-        m[0] = fmaf(r4, r4, r66);
-        m[1] = (r4 + r5) * r6;
-        m[2] = fmaf(r5, r5, r66);
-        m[3] = fmaf(r4, r2, r6 * r3);
-        m[4] = fmaf(r6, r2, r5 * r3);
-    } else {
-        m[0] = r4 * r4 + r6 * r6;
-        m[1] = (r4 + r5) * r6;
-        m[2] = r5 * r5 + r6 * r6;
-        m[3] = r4 * r2 + r6 * r3;
-        m[4] = r6 * r2 + r5 * r3;
-    }
-}
-
 template <bool UF>
 __device__ __forceinline__ void upd_compute(const UpdLoad &L, int w, int h, int x, int y, float dx, float dy, float m[5])
 {
@@ -1067,21 +987,6 @@ __device__ __forceinline__ void update_matrices_px(const float *__restrict__ R0,
     UpdLoad L;
     upd_load(R0, R1, pitch, w, h, x, y, dx, dy, L);
     upd_compute<UF>(L, w, h, x, y, dx, dy, m);
-}
-
-__device__ __forceinline__ void solve2x2(float g11f, float g12f, float g22f, float h1f, float h2f, float &fx, float &fy)
-{
-    double g11 = g11f, g12 = g12f, g22 = g22f, h1 = h1f, h2 = h2f;
-    double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
-    fx = (float)((g11 * h2 - g12 * h1) * idet);
-    fy = (float)((g22 * h1 - g12 * h2) * idet);
-}
-
-__device__ __forceinline__ void solve2x2d(double g11, double g12, double g22, double h1, double h2, float &fx, float &fy)
-{
-    double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
-    fx = (float)((g11 * h2 - g12 * h1) * idet);
-    fy = (float)((g22 * h1 - g12 * h2) * idet);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1507,44 +1412,6 @@ __global__ void __launch_bounds__(256, 2) gauss_iter_kernel(IterArgs a, WinTaps 
     gauss_epilogue<UF>(a, Fb, tid, x0, y0, b, pitch);
 }
 
-
-// Packed f32x2 arithmetic (sm_100+), written as PTX with explicit .rn so that neither NVVM nor ptxas may contract a
-// multiply and an add into an FFMA2: each half is one IEEE-754 operation, exactly like the scalar oracle code.
-// (The CUDA intrinsics __fmul2_rn + __fadd2_rn WERE contracted into FFMA2 by nvcc 12.9 even with -fmad=false.)
-__device__ __forceinline__ unsigned long long f2_pack(float2 v)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
-    return r;
-}
-__device__ __forceinline__ float2 f2_unpack(unsigned long long r)
-{
-    float2 v;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
-    return v;
-}
-__device__ __forceinline__ float2 tw_add2(float2 a, float2 b)
-{
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-    return f2_unpack(d);
-}
-__device__ __forceinline__ float2 tw_mul2(float2 a, float2 b)
-{
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-    return f2_unpack(d);
-}
-// NOTE: ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2 even with --fmad false (the scalar
-// mul.rn/add.rn pair is respected).  The faithful accumulate "v + p" is therefore issued as fma(p, one, v) with
-// `one` a RUNTIME 1.0f (WinTaps.one): p * 1.0 is exact, so the result is round(p + v) -- one IEEE add -- and ptxas
-// cannot fold it because it does not know the value.
-__device__ __forceinline__ float2 tw_fma2(float2 a, float2 b, float2 c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
-    return f2_unpack(d);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K4/K5 v2: the same tile / phase structure as gauss_iter_kernel, with the tap sums issued as PACKED f32x2

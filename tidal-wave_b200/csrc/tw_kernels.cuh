@@ -98,6 +98,15 @@ struct IterArgs {
     int ufma; // validated relaxation: fmaf chains in the update-matrices arithmetic (oracle relax bit 6)
 };
 cudaError_t launch_gauss_iter(cudaStream_t s, const IterArgs &a, const WinTaps &t);
+// K4/K5 for window radius 15: the persistent, warp-specialised strip kernel (tw_window.cu).  Its operands arrive through
+// TMA tensor maps (cuTensorMapEncodeTiled) built once per (scale, M buffer): make_strip_maps.
+struct StripMaps {
+    alignas(64) unsigned char opaque[6 * 128]; // six CUtensorMap: M channel-pair / h2 rows (1-row and 8-row boxes), R0 tiles, R1 row chunks
+    int valid;
+};
+bool make_strip_maps(const float *M, const float *R, const LevelDims &d, int batch, StripMaps *out);
+bool gauss_strip_ok(const IterArgs &a, const WinTaps &t);
+cudaError_t launch_gauss_strip(cudaStream_t s, const IterArgs &a, const WinTaps &t, const StripMaps &m);
 // K5s: last iteration of the finest scale evaluated only at the span-grid points (needs a.span, a.thr2, a.counts; writes the
 // sampled (dx, dy) at their positions of a.flow and nothing else).  gauss_last_sparse_ok: whether this geometry is supported.
 bool gauss_last_sparse_ok(const IterArgs &a, const WinTaps &t);

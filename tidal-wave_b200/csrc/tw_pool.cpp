@@ -93,8 +93,9 @@ void consumer_main(tw_pool *p, int idx)
         p->ready.fetch_add(1);
     }
     p->cv_res.notify_all();
-    const int cap = p->vector_cap;
-    std::vector<tw_vector> vec((size_t)p->batch * std::max(cap, 1));
+    // vector_cap > 0: at most that many vectors are kept per request; vector_cap == 0: every vector of every request (the
+    // reference returns them all, src/consumer.cpp:60-76) -- the capacity then follows each request's own sampling grid
+    std::vector<tw_vector> vec;
     std::vector<tw_result> res(p->batch);
     std::vector<Request> work;
     std::vector<const uint8_t *> ex(p->batch), tg(p->batch);
@@ -126,6 +127,9 @@ void consumer_main(tw_pool *p, int idx)
             p->cv_res.notify_all();
             continue;
         }
+        int cap = p->vector_cap;
+        if (cap <= 0) cap = std::max(1, ((work[0].ew + p->span - 1) / p->span) * ((work[0].eh + p->span - 1) / p->span));
+        if (vec.size() < work.size() * (size_t)cap) vec.resize(work.size() * (size_t)cap);
         if (work.size() == 1) {
             const Request &r = work[0];
             tw_compare(ctx, r.expect, r.ew, r.eh, r.target, r.tw, r.th, &p->param, p->threshold, p->span, vec.data(), cap, &res[0]);

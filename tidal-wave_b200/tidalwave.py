@@ -59,8 +59,8 @@ class TidalWave:
             from .api import load
             ndev = max(1, load().tw_device_count())
             devices = self._devices or [i % ndev for i in range(max(1, self.numThreads))]  # consumer i <-> GPU i % count
-            self._pool = Pool(devices, self.param, self.threshold, self.span, max_w=w, max_h=h, batch=self._batch,
-                              vector_cap=((w + self.span - 1) // self.span + 1) * ((h + self.span - 1) // self.span + 1))
+            # screenshot directories mix page sizes: no size bound, and every vector of every pair comes back whatever its size
+            self._pool = Pool(devices, self.param, self.threshold, self.span, max_w=0, max_h=0, batch=self._batch, vector_cap=0)
         return self._pool
 
     def calc(self, expected: str, target: str):
@@ -116,7 +116,8 @@ class TidalWave:
                 self._emit("error", {"status": "ERROR", "reason": err})  # src/broker.cpp:57-70
             else:
                 self._report["data"] += 1
-                r.pop("n_vectors", None)
+                if r.pop("n_vectors", len(r["vector"])) != len(r["vector"]):
+                    raise RuntimeError("dispatcher returned a truncated vector list")  # cannot happen with vector_cap = 0
                 r["expect_image"], r["target_image"] = expected, target
                 self._emit("data", r)                                    # src/broker.cpp:44-55,161-188
 
