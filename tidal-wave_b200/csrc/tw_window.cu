@@ -1,29 +1,33 @@
 // tw_window.cu -- K4 / K5 for the Gaussian window of radius 15 (winSize 30 / 31, the reference's default): ONE persistent,
-// warp-specialised CTA per SM that slides down 96-column strips of the M planes.
+// warp-specialised CTA per SM that slides down 64-column strips of the M planes.
 //
 //   Farneback stages A.5 (window blur of the five M planes + 2x2 solve) and A.4 (next update-matrices) of SURVEY App. A --
 //   the per-iteration body of cv::calcOpticalFlowFarneback, /root/reference/src/opticalflow.cpp:83-85 -- fused into one
 //   pass: per iteration M (20 B/px), R0 (20), R1 (20) are read once and M' (20) is written once.
 //
-// Roles of the 16 warps of a CTA (one CTA per SM, 128 registers per thread, 208 KB of shared memory):
-//   warps 0-9    V walkers: thread = (column, channel pair) [warps 0-7] or (column pair, h2) [warps 8-9].  Each keeps a 40-row
-//                sliding window of its column in REGISTERS for the whole strip, so an M row is read from L2 exactly once per
-//                strip (the tile kernel re-read it 1.94x) and there is no cold start per tile; per 8-row group: 8 new rows
-//                from the M ring, 8 outputs x 31 taps as packed f32x2 (FFMA2), taps in the oracle's order -> the P ring.
-//   warps 10-15  H + solve + U: horizontal taps from the P ring (lane = row x 4-pixel quad, conflict-free LDS.128), 2x2 solve in
-//                double -> flow tile in shared memory; then (not last) the next update matrices (A.4) with R0 / R1 read from
-//                shared memory, two vertically adjacent pixels per packed f32x2 instruction on the warp-uniform fast path
-//                (all pixels inside, within the staged R1 window, off the damped frame border), a scalar per-pixel path
-//                otherwise (pixels whose displaced position leaves the staged window -- large motion -- gather from global
-//                memory; same values, same arithmetic) -> M' stores; (last) flow stores + the fused span-grid threshold count.
-//   TMA producers  tensor-map bulk copies (cp.async.bulk.tensor, UTMALDG), issued as far ahead as the rings allow by
-//                lane 0 of warp 8 (the M rows: 8-row chunks, one 8-row box per plane; at the frame top / bottom one row per
-//                copy with the row coordinate clamped = the replicate border of App. A.5; 3-slot ring) and lane 0 of warp 9
-//                (the R0 tile of each group, 96 x 8 x 5 channels, 2 slots; the R1 rows its bilinear gather can touch, 104
-//                columns x rows y-8 .. y+15, a 4-chunk row ring).  Out-of-frame parts are zero-filled by the TMA unit and
-//                never read.  Both poll (mbarrier.test_wait) and never block, so no producer can stall a pipeline stage.
-//   All hand-offs are mbarrier pipelines (full / empty per ring slot); the H -> U hand-off inside warps 10-15 is a named
-//   barrier.  Every wait sleeps between probes and traps after ~2 s instead of hanging the device.
+// Roles of the 16 warps of a CTA (one CTA per SM, 128 registers per thread, ~215 KB of shared memory).  Every scheduler of
+// the SM holds two V warps and two H / U warps, so the FFMA2-dense vertical pass and the load / FP64 / address-heavy solve and
+// update passes share each issue port:
+//   warps 0-7    V walkers: thread = (column, channel pair) [warps 0-5] or (column pair, h2) [warps 6-7, 48 lanes].  Each keeps a
+//                40-row sliding window of its column in REGISTERS for the whole strip, so an M row is read from L2 exactly once
+//                per strip and there is no cold start per tile; per 8-row group: 8 new rows from the M ring, 8 outputs x 31
+//                taps as packed f32x2 (FFMA2), taps in the oracle's order -> the P ring.
+//   warps 8-15   two teams of four warps that take alternate groups, each H + solve + U: horizontal taps from the P ring (lane =
+//                row x 4-pixel quad, conflict-free LDS.128), 2x2 solve in double -> the team's flow tile in shared memory; then
+//                (not last) the next update matrices (A.4) with R0 / R1 read from shared memory, two vertically adjacent pixels
+//                per packed f32x2 instruction on the warp-uniform fast path (all pixels inside, within the staged R1 window,
+//                off the damped frame border), a scalar per-pixel path otherwise (pixels whose displaced position leaves the
+//                staged window -- large motion -- gather from global memory; same values, same arithmetic) -> M' stores;
+//                (last) flow stores + the fused span-grid threshold count.
+//   TMA          tensor-map bulk copies (cp.async.bulk.tensor, UTMALDG) into three rings: the M rows (8-row chunks, one 8-row box
+//                per plane; at the frame top / bottom one row per copy with the row coordinate clamped = the replicate border
+//                of App. A.5), the R0 tile of each group (64 x 8 x 5 channels) and the R1 rows its bilinear gather can touch
+//                (72 columns x rows y-8 .. y+15, a 6-chunk row ring).  There is no producer warp and nobody polls: the LAST
+//                consumer of a ring slot (a shared-memory counter tells which warp that is) issues the copy that refills it,
+//                NM / NR0 / NR1 chunks ahead in the CTA's unit sequence.  Out-of-frame parts are zero-filled by the TMA unit and
+//                never read.
+//   Hand-offs: "full" mbarriers (TMA transaction bytes; V -> H arrivals), an "empty" mbarrier per P slot, the consumer counters
+//   above, and one 128-thread named barrier per team between H and U.  Every wait traps after ~2 s instead of hanging.
 //
 // Arithmetic per output is exactly that of gauss_iter2_kernel (tw_kernels.cu): FMA = 0 the oracle's add-mul-add order
 // (bit-identical to oracle/farneback_ref.c), FMA = 2 the direct-form fmaf taps of the relaxed default (oracle relax bit 7).
@@ -32,51 +36,57 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace tw {
 
 namespace {
 
-constexpr int WS_SW = 96;                 // output columns per strip
+constexpr int WS_SW = 64;                 // output columns per strip
 constexpr int WS_XH = 16;                 // left halo of the V columns (15 needed, 16 keeps the copies 64-byte aligned)
-constexpr int WS_VC = WS_SW + 2 * WS_XH;  // 128 V columns
+constexpr int WS_VC = WS_SW + 2 * WS_XH;  // 96 V columns
 constexpr int WS_G = 8;                   // rows per group
 constexpr int WS_MR = 15;
 constexpr int WS_WIN = 40;                // register window rows = 5 chunks
-constexpr int WS_NM = 3, WS_NP = 2, WS_NR0 = 2, WS_NR1 = 4, WS_NF = 2;
+constexpr int WS_NM = 3, WS_NP = 3, WS_NR0 = 3, WS_NR1 = 6, WS_NF = 4; // WS_NF: 2 teams x 2 slots
 constexpr int WS_MPROW = 2 * WS_VC * 4, WS_MHROW = WS_VC * 4;         // bytes per staged row of a channel-pair plane / of the h2 plane
 constexpr int WS_MP1OFF = WS_G * WS_MPROW, WS_MHOFF = 2 * WS_MP1OFF;  // chunk layout: pair01[8 rows] | pair23[8 rows] | h2[8 rows]
-constexpr int WS_MCHUNK = WS_MHOFF + WS_G * WS_MHROW;                 // 20480
-constexpr int WS_P2 = 130, WS_P4 = 132;                               // float2 / float pitches of the P planes
-constexpr int WS_P23OFF = WS_G * WS_P2 * 8, WS_P4OFF = 2 * WS_P23OFF; // 8320, 16640
-constexpr int WS_PSLOT = WS_P4OFF + WS_G * WS_P4 * 4;                 // 20864
-constexpr int WS_R0SLOT = WS_G * 5 * WS_SW * 4;                       // 15360
-constexpr int WS_R1C = 104, WS_R1X = 4;                               // staged R1 columns: x0 - 4 .. x0 + 99
+constexpr int WS_MCHUNK = WS_MHOFF + WS_G * WS_MHROW;                 // 15360
+constexpr int WS_P2 = 98, WS_P4 = 100;                                // float2 / float pitches of the P planes (= 4 words mod 32)
+constexpr int WS_P23OFF = WS_G * WS_P2 * 8, WS_P4OFF = 2 * WS_P23OFF; // 6272, 12544
+constexpr int WS_PSLOT = WS_P4OFF + WS_G * WS_P4 * 4;                 // 15744
+constexpr int WS_R0SLOT = WS_G * 5 * WS_SW * 4;                       // 10240
+constexpr int WS_R1C = 72, WS_R1X = 4;                                // staged R1 columns: x0 - 4 .. x0 + 67
 constexpr int WS_R1ROW = 5 * WS_R1C;                                  // floats per ring row
-constexpr int WS_R1CHUNK = WS_G * WS_R1ROW * 4;                       // 16640
-constexpr int WS_FP = 97;                                             // flow tile pitch
-constexpr int WS_FSLOT = 2 * WS_G * WS_FP * 4;                        // 6208
+constexpr int WS_R1CHUNK = WS_G * WS_R1ROW * 4;                       // 11520
+constexpr int WS_R1RING = WS_NR1 * WS_G;                              // ring rows
+constexpr int WS_FP = 65;                                             // flow tile pitch
+constexpr int WS_FSLOT = 2 * WS_G * WS_FP * 4;                        // 4352
 
 constexpr int WS_OFF_M = 0;
-constexpr int WS_OFF_P = WS_OFF_M + WS_NM * WS_MCHUNK;      // 61440
-constexpr int WS_OFF_R0 = WS_OFF_P + WS_NP * WS_PSLOT;      // 103168
-constexpr int WS_OFF_R1 = WS_OFF_R0 + WS_NR0 * WS_R0SLOT;   // 133888
-constexpr int WS_OFF_F = WS_OFF_R1 + WS_NR1 * WS_R1CHUNK;   // 200448
-constexpr int WS_OFF_BAR = WS_OFF_F + WS_NF * WS_FSLOT;     // 212864
-constexpr int WS_NBAR = 2 * (WS_NM + WS_NP + WS_NR0 + WS_NR1);
+constexpr int WS_OFF_P = WS_OFF_M + WS_NM * WS_MCHUNK;
+constexpr int WS_OFF_R0 = WS_OFF_P + WS_NP * WS_PSLOT;
+constexpr int WS_OFF_R1 = WS_OFF_R0 + WS_NR0 * WS_R0SLOT;
+constexpr int WS_OFF_F = WS_OFF_R1 + WS_NR1 * WS_R1CHUNK;
+constexpr int WS_OFF_BAR = WS_OFF_F + WS_NF * WS_FSLOT;
+constexpr int WS_NBAR = 2 * (WS_NM + WS_NP + WS_NR0 + WS_NR1); // full / empty per ring slot
 constexpr int WS_SMEM = WS_OFF_BAR + WS_NBAR * 8;
-static_assert(WS_OFF_R0 % 128 == 0 && WS_OFF_R1 % 128 == 0 && WS_R0SLOT % 128 == 0 && WS_R1CHUNK % 128 == 0 && WS_MPROW % 128 == 0 && WS_MHROW % 128 == 0,
+static_assert(WS_OFF_P % 128 == 0 && WS_OFF_R0 % 128 == 0 && WS_OFF_R1 % 128 == 0 && WS_R0SLOT % 128 == 0 && WS_R1CHUNK % 128 == 0 &&
+                  WS_MPROW % 128 == 0 && WS_MHROW % 128 == 0 && WS_MCHUNK % 128 == 0,
               "TMA destinations are 128-byte aligned");
-static_assert(WS_OFF_BAR % 8 == 0 && WS_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(WS_OFF_F % 16 == 0 && WS_OFF_BAR % 8 == 0 && WS_SMEM <= 227 * 1024, "shared memory budget");
 
-constexpr int WS_NVW = 10, WS_NHW = 6;                 // V walker warps, H / U warps
-constexpr int WS_THREADS = (WS_NVW + WS_NHW) * 32;     // 512: the register file of an SM at 128 registers per thread
-constexpr int WS_HU_THREADS = WS_NHW * 32;
+constexpr int WS_NVW = 8, WS_NHW = 8;                  // V walker warps, H / U warps (two teams of WS_TEAMW)
+constexpr int WS_TEAMW = 4, WS_TEAM_THREADS = WS_TEAMW * 32;
+constexpr int WS_VLANES = 2 * WS_VC + WS_VC / 2;       // 240 walkers
+constexpr int WS_PRODW = WS_NVW + WS_NHW;              // the producer warp; it and the three spare warps of its warpgroup give their
+constexpr int WS_THREADS = (WS_NVW + WS_NHW + 4) * 32; // registers to the other sixteen (setmaxnreg): 640 threads launched at 96
+constexpr int WS_REGS_WORK = 112, WS_REGS_PROD = 24;
 
 // barrier indices
 constexpr int B_FULLM = 0, B_EMPTYM = B_FULLM + WS_NM, B_FULLP = B_EMPTYM + WS_NM, B_EMPTYP = B_FULLP + WS_NP,
-              B_FULLR0 = B_EMPTYP + WS_NP, B_EMPTYR0 = B_FULLR0 + WS_NR0, B_FULLR1 = B_EMPTYR0 + WS_NR0,
-              B_EMPTYR1 = B_FULLR1 + WS_NR1;
+              B_FULLR0 = B_EMPTYP + WS_NP, B_EMPTYR0 = B_FULLR0 + WS_NR0, B_FULLR1 = B_EMPTYR0 + WS_NR0, B_EMPTYR1 = B_FULLR1 + WS_NR1;
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
@@ -99,30 +109,9 @@ __device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity)
                  : "memory");
     return done;
 }
-// try_wait with a suspend-time hint: the warp may sleep in hardware for up to `ns` before the instruction returns
-__device__ __forceinline__ unsigned mbar_try_sleep(unsigned bar, unsigned parity, unsigned ns)
-{
-    unsigned done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity), "r"(ns)
-                 : "memory");
-    return done;
-}
-// non-blocking probe (the producers poll with it)
-__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
-{
-    unsigned done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    return done;
-}
 // Waits for the phase with the given parity: try_wait suspends the warp in hardware for a short, implementation-defined time
-// and is simply repeated.  (A version that slept between probes -- suspend-time hint + nanosleep -- woke the V walkers late
-// enough that the H / U warps ran out of P slots 13 % of the time.)  A wait of more than ~2 s means a broken pipeline: trap
-// (the launch fails with an error) instead of hanging the device.
+// and is simply repeated.  A wait of more than ~2 s means a broken pipeline: trap (the launch fails with an error) instead of
+// hanging the device.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     if (mbar_try(bar, parity)) return;
@@ -142,11 +131,27 @@ __device__ __forceinline__ float lds32(unsigned addr)
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds64(unsigned addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts64(unsigned addr, float2 v)
 {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
-__device__ __forceinline__ void hu_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(WS_HU_THREADS) : "memory"); }
+// non-blocking probe (the producer polls with it)
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return done;
+}
+__device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(WS_TEAM_THREADS) : "memory"); }
 
 struct Unit {
     int b, x0, y0, ng;
@@ -163,9 +168,23 @@ struct StripArgs {
     int span;
     double thr2;
     int *counts;
+    int dbg; // TW_STRIP_DEBUG builds only: bit 0 skip the V taps, bit 1 skip H + solve, bit 3 skip U
+    unsigned *prof; // TW_STRIP_DEBUG builds only: [grid][16 warps][8] phase clocks
 };
 
 namespace {
+
+#ifdef TW_STRIP_DEBUG
+#define WS_DBG(bit) (a.dbg & (bit))
+#define WS_PROF_DECL unsigned pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0_ = clock();
+#define WS_PROF(i) { const unsigned t1_ = clock(); pacc_[i] += t1_ - pt0_; pt0_ = t1_; }
+#define WS_PROF_DUMP if (a.prof && lane == 0) for (int i_ = 0; i_ < 8; i_++) a.prof[(blockIdx.x * 16 + warp) * 8 + i_] = pacc_[i_];
+#else
+#define WS_DBG(bit) 0
+#define WS_PROF_DECL
+#define WS_PROF(i)
+#define WS_PROF_DUMP
+#endif
 
 __device__ __forceinline__ Unit decode_unit(const StripArgs &a, int u)
 {
@@ -179,20 +198,22 @@ __device__ __forceinline__ Unit decode_unit(const StripArgs &a, int u)
     return U;
 }
 
-// ---- TMA producers: streams that run across the CTA's unit sequence; pump() issues while a ring slot is free ----
-// M rows: every unit contributes ng + 4 chunks of 8 rows (rows y0 - 15 + 8c ..).
-struct MStream {
+// ---- TMA producer: three streams that run across the CTA's unit sequence; each pump issues while a ring slot is free ----
+// M rows: every unit contributes ng + 4 chunks of 8 rows (rows y0 - 15 + 8c ..); R0 tiles: one per group; R1 row chunks: ng + 2
+// per unit (rows y0 - 8 + 8c .. + 7 of the target image's expansion).
+struct Stream {
     int u, c;
     Unit U;
     unsigned n; // chunks issued so far
 };
 
-__device__ __noinline__ void mstream_pump(MStream &ms, const StripArgs &a, unsigned smem, const CUtensorMap *mp1, const CUtensorMap *mh1,
-                                          const CUtensorMap *mp8, const CUtensorMap *mh8)
+__device__ __forceinline__ bool pump_m(Stream &ms, const StripArgs &a, unsigned smem, const CUtensorMap *mp1, const CUtensorMap *mh1,
+                                       const CUtensorMap *mp8, const CUtensorMap *mh8)
 {
+    bool any = false;
     while (ms.u < a.nunits) {
         const unsigned s = ms.n % WS_NM;
-        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYM + s), ((ms.n / WS_NM) & 1) ^ 1)) return;
+        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYM + s), ((ms.n / WS_NM) & 1) ^ 1)) break;
         const unsigned bar = smem + WS_OFF_BAR + 8 * (B_FULLM + s);
         mbar_expect_tx(bar, WS_MCHUNK);
         const unsigned dst = smem + WS_OFF_M + s * WS_MCHUNK;
@@ -211,6 +232,7 @@ __device__ __noinline__ void mstream_pump(MStream &ms, const StripArgs &a, unsig
                 tma_load_3d(dst + WS_MHOFF + r * WS_MHROW, mh1, 4 * pitch + xs, y, ms.U.b, bar);
             }
         }
+        any = true;
         ms.n++;
         if (++ms.c == ms.U.ng + 4) {
             ms.c = 0;
@@ -218,81 +240,80 @@ __device__ __noinline__ void mstream_pump(MStream &ms, const StripArgs &a, unsig
             if (ms.u < a.nunits) ms.U = decode_unit(a, ms.u);
         }
     }
+    return any;
 }
 
-// R0 tiles (one per group) and R1 row chunks (ng + 2 per unit: rows y0 - 8 + 8c .. + 7 of the target image's expansion).
-struct RStream {
-    int u0, g0, u1, c1;
-    Unit U0, U1;
-    unsigned n0, n1;
-};
-
-__device__ __noinline__ void rstream_pump(RStream &rs, const StripArgs &a, unsigned smem, const CUtensorMap *r0map, const CUtensorMap *r1map)
+__device__ __forceinline__ bool pump_r0(Stream &rs, const StripArgs &a, unsigned smem, const CUtensorMap *r0map)
 {
-    while (rs.u0 < a.nunits) {
-        const unsigned s = rs.n0 % WS_NR0;
-        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYR0 + s), ((rs.n0 / WS_NR0) & 1) ^ 1)) break;
+    bool any = false;
+    while (rs.u < a.nunits) {
+        const unsigned s = rs.n % WS_NR0;
+        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYR0 + s), ((rs.n / WS_NR0) & 1) ^ 1)) break;
         const unsigned bar = smem + WS_OFF_BAR + 8 * (B_FULLR0 + s);
         mbar_expect_tx(bar, WS_R0SLOT);
-        tma_load_3d(smem + WS_OFF_R0 + s * WS_R0SLOT, r0map, rs.U0.x0, 5 * (rs.U0.y0 + WS_G * rs.g0), 2 * rs.U0.b, bar);
-        rs.n0++;
-        if (++rs.g0 == rs.U0.ng) {
-            rs.g0 = 0;
-            rs.u0 += gridDim.x;
-            if (rs.u0 < a.nunits) rs.U0 = decode_unit(a, rs.u0);
+        tma_load_3d(smem + WS_OFF_R0 + s * WS_R0SLOT, r0map, rs.U.x0, 5 * (rs.U.y0 + WS_G * rs.c), 2 * rs.U.b, bar);
+        any = true;
+        rs.n++;
+        if (++rs.c == rs.U.ng) {
+            rs.c = 0;
+            rs.u += gridDim.x;
+            if (rs.u < a.nunits) rs.U = decode_unit(a, rs.u);
         }
     }
-    while (rs.u1 < a.nunits) {
-        const unsigned s = rs.n1 % WS_NR1;
-        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYR1 + s), ((rs.n1 / WS_NR1) & 1) ^ 1)) break;
-        const unsigned bar = smem + WS_OFF_BAR + 8 * (B_FULLR1 + s);
-        mbar_expect_tx(bar, WS_R1CHUNK);
-        tma_load_3d(smem + WS_OFF_R1 + s * WS_R1CHUNK, r1map, rs.U1.x0 - WS_R1X, 5 * (rs.U1.y0 - WS_G + WS_G * rs.c1), 2 * rs.U1.b + 1, bar);
-        rs.n1++;
-        if (++rs.c1 == rs.U1.ng + 2) {
-            rs.c1 = 0;
-            rs.u1 += gridDim.x;
-            if (rs.u1 < a.nunits) rs.U1 = decode_unit(a, rs.u1);
-        }
-    }
+    return any;
 }
 
-// The per-thread view of a V walker: two source words per staged row (srcA, srcB: the clamped columns) and one float2 output.
-struct VLane {
-    unsigned srcA, srcB, rstride, dst, dstride;
-};
+__device__ __forceinline__ bool pump_r1(Stream &rs, const StripArgs &a, unsigned smem, const CUtensorMap *r1map)
+{
+    bool any = false;
+    while (rs.u < a.nunits) {
+        const unsigned s = rs.n % WS_NR1;
+        if (!mbar_test(smem + WS_OFF_BAR + 8 * (B_EMPTYR1 + s), ((rs.n / WS_NR1) & 1) ^ 1)) break;
+        const unsigned bar = smem + WS_OFF_BAR + 8 * (B_FULLR1 + s);
+        mbar_expect_tx(bar, WS_R1CHUNK);
+        tma_load_3d(smem + WS_OFF_R1 + s * WS_R1CHUNK, r1map, rs.U.x0 - WS_R1X, 5 * (rs.U.y0 - WS_G + WS_G * rs.c), 2 * rs.U.b + 1, bar);
+        any = true;
+        rs.n++;
+        if (++rs.c == rs.U.ng + 2) {
+            rs.c = 0;
+            rs.u += gridDim.x;
+            if (rs.u < a.nunits) rs.U = decode_unit(a, rs.u);
+        }
+    }
+    return any;
+}
 
 // 8 outputs x 31 taps of one walker from its register window (rows 8g .. 8g + 39 of the unit's M rows) -> P slot.
 template <int FMA>
-__device__ __forceinline__ void v_compute(const float2 (&win)[WS_WIN], unsigned pslot, const VLane &vl, const WinTaps &t)
+__device__ __forceinline__ void v_compute(const float2 (&win)[WS_WIN], unsigned pd, unsigned dstride, const WinTaps &t, bool store)
 {
-    constexpr int J = 0;
     const float2 one2 = make_float2(t.one, t.one);
     float2 v[WS_G];
 #pragma unroll
-    for (int o = 0; o < WS_G; o++) v[o] = tw_mul2(win[(8 * J + o + WS_MR) % WS_WIN], make_float2(t.k[0], t.k[0]));
+    for (int o = 0; o < WS_G; o++) v[o] = tw_mul2(win[o + WS_MR], make_float2(t.k[0], t.k[0]));
 #pragma unroll
     for (int i = 1; i <= WS_MR; i++) {
         const float2 kk = make_float2(t.k[i], t.k[i]);
         if (FMA == 2) { // direct form (oracle relax bit 7): upper row first
 #pragma unroll
-            for (int o = 0; o < WS_G; o++) v[o] = tw_fma2(win[(8 * J + o + WS_MR - i) % WS_WIN], kk, v[o]);
+            for (int o = 0; o < WS_G; o++) v[o] = tw_fma2(win[o + WS_MR - i], kk, v[o]);
 #pragma unroll
-            for (int o = 0; o < WS_G; o++) v[o] = tw_fma2(win[(8 * J + o + WS_MR + i) % WS_WIN], kk, v[o]);
+            for (int o = 0; o < WS_G; o++) v[o] = tw_fma2(win[o + WS_MR + i], kk, v[o]);
         } else {
 #pragma unroll
             for (int o = 0; o < WS_G; o++) {
-                const float2 sum = tw_add2(win[(8 * J + o + WS_MR + i) % WS_WIN], win[(8 * J + o + WS_MR - i) % WS_WIN]);
+                const float2 sum = tw_add2(win[o + WS_MR + i], win[o + WS_MR - i]);
                 v[o] = tw_fma2(tw_mul2(sum, kk), one2, v[o]); // = v + round(sum * k): see tw_fma2 in tw_device.cuh
             }
         }
     }
-    const unsigned pd = pslot + vl.dst;
+    if (store) {
 #pragma unroll
-    for (int o = 0; o < WS_G; o++) sts64(pd + o * vl.dstride, v[o]);
+        for (int o = 0; o < WS_G; o++) sts64(pd + o * dstride, v[o]);
+    }
 }
 
-// Horizontal taps + solve for 4 adjacent pixels of one row (P slot pointers already offset to the row).
+// Horizontal taps + solve for 4 adjacent pixels of one row (P slot pointers already offset to the row and the quad).
 template <int FMA>
 __device__ __forceinline__ void h_quad(const float2 *__restrict__ p01, const float2 *__restrict__ p23, const float *__restrict__ p4, const WinTaps &t,
                                        float (&fx)[4], float (&fy)[4])
@@ -379,74 +400,76 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
     const size_t plane = a.d.plane;
 
     if (tid == 0) {
+        // R1 chunks are released by both teams (each arrives once per warp after its last use of the chunk, twice where the
+        // other team never reads it): 2 x WS_TEAMW arrivals
         for (int i = 0; i < WS_NM; i++) { mbar_init(bars + 8 * (B_FULLM + i), 1); mbar_init(bars + 8 * (B_EMPTYM + i), WS_NVW); }
-        for (int i = 0; i < WS_NP; i++) { mbar_init(bars + 8 * (B_FULLP + i), WS_NVW); mbar_init(bars + 8 * (B_EMPTYP + i), WS_NHW); }
-        for (int i = 0; i < WS_NR0; i++) { mbar_init(bars + 8 * (B_FULLR0 + i), 1); mbar_init(bars + 8 * (B_EMPTYR0 + i), WS_NHW); }
-        for (int i = 0; i < WS_NR1; i++) { mbar_init(bars + 8 * (B_FULLR1 + i), 1); mbar_init(bars + 8 * (B_EMPTYR1 + i), WS_NHW); }
+        for (int i = 0; i < WS_NP; i++) { mbar_init(bars + 8 * (B_FULLP + i), WS_NVW); mbar_init(bars + 8 * (B_EMPTYP + i), WS_TEAMW); }
+        for (int i = 0; i < WS_NR0; i++) { mbar_init(bars + 8 * (B_FULLR0 + i), 1); mbar_init(bars + 8 * (B_EMPTYR0 + i), WS_TEAMW); }
+        for (int i = 0; i < WS_NR1; i++) { mbar_init(bars + 8 * (B_FULLR1 + i), 1); mbar_init(bars + 8 * (B_EMPTYR1 + i), 2 * WS_TEAMW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp < WS_NVW) {
-        // ================= V walkers; lane 0 of warps 8 / 9 carries the TMA producers =================
-        const bool m_prod = tid == 8 * 32, r_prod = !LAST && tid == 9 * 32;
-        MStream ms;
-        RStream rs;
-        if (m_prod) {
-            ms.u = blockIdx.x; ms.c = 0; ms.n = 0;
-            if (ms.u < a.nunits) ms.U = decode_unit(a, ms.u);
-        }
-        if (r_prod) {
-            rs.u0 = rs.u1 = blockIdx.x; rs.g0 = rs.c1 = 0; rs.n0 = rs.n1 = 0;
-            if (rs.u0 < a.nunits) rs.U0 = rs.U1 = decode_unit(a, rs.u0);
-        }
-        auto pump = [&]() {
-            if (m_prod) mstream_pump(ms, a, smem, &mapMp, &mapMh, &mapMp8, &mapMh8);
-            if (r_prod) rstream_pump(rs, a, smem, &mapR0, &mapR1);
-        };
-        // a producer lane keeps its stream going while its warp waits; the other warps sleep in mbar_wait
-        auto wait = [&](unsigned bar, unsigned parity) {
-            if (warp >= 8) {
-                if (lane == 0) {
-                    unsigned it = 0;
-                    while (!mbar_test(bar, parity)) {
-                        pump();
-                        if (++it > (1u << 26)) __trap();
-                    }
-                }
-                __syncwarp();
+    if (warp >= WS_PRODW) {
+        // ================= TMA producer (one lane); its warpgroup hands its registers to the working warps =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_PROD));
+        if (warp != WS_PRODW || lane != 0) return;
+        Stream ms, r0, r1;
+        ms.u = r0.u = r1.u = blockIdx.x; ms.c = r0.c = r1.c = 0; ms.n = r0.n = r1.n = 0;
+        if (ms.u < a.nunits) ms.U = r0.U = r1.U = decode_unit(a, ms.u);
+        if (LAST) r0.u = r1.u = a.nunits;
+        unsigned idle = 0;
+        while (ms.u < a.nunits || r0.u < a.nunits || r1.u < a.nunits) {
+            bool any = pump_m(ms, a, smem, &mapMp, &mapMh, &mapMp8, &mapMh8);
+            if (!LAST) {
+                any |= pump_r1(r1, a, smem, &mapR1);
+                any |= pump_r0(r0, a, smem, &mapR0);
             }
-            mbar_wait(bar, parity);
-        };
-        pump();
+            if (any) idle = 0;
+            else if (++idle > (1u << 24)) __trap();
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_WORK));
 
+    if (warp < WS_NVW) {
+        // ================= V walkers =================
+        const bool pairlane = tid < 2 * WS_VC, active = tid < WS_VLANES;
         unsigned nM = 0, nP = 0; // chunks consumed, groups blurred (global over the CTA's units)
+        WS_PROF_DECL
         for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
             const Unit U = decode_unit(a, u);
             const int xs = U.x0 - WS_XH;
-            VLane vl;
-            if (tid < 2 * WS_VC) { // (column, channel pair)
-                const int pair = tid >> 7, j = tid & (WS_VC - 1);
+            unsigned srcA, srcB, dst, dstride;
+            if (pairlane) { // (column, channel pair)
+                const int pair = tid >= WS_VC, j = tid - pair * WS_VC;
                 const int cj = clampi(xs + j, 0, w - 1) - xs;
-                vl.srcA = pair * WS_MP1OFF + cj * 8; vl.srcB = vl.srcA + 4; vl.rstride = WS_MPROW;
-                vl.dst = (pair ? WS_P23OFF : 0) + j * 8; vl.dstride = WS_P2 * 8;
-            } else { // (column pair, h2)
-                const int jj = tid - 2 * WS_VC;
+                srcA = pair * WS_MP1OFF + cj * 8; srcB = srcA + 4;
+                dst = (pair ? WS_P23OFF : 0) + j * 8; dstride = WS_P2 * 8;
+            } else { // (column pair, h2); the 16 spare lanes of warp 7 shadow the last walker and do not store
+                const int jj = min(tid - 2 * WS_VC, WS_VC / 2 - 1);
                 const int ca = clampi(xs + 2 * jj, 0, w - 1) - xs, cb = clampi(xs + 2 * jj + 1, 0, w - 1) - xs;
-                vl.srcA = WS_MHOFF + ca * 4; vl.srcB = WS_MHOFF + cb * 4; vl.rstride = WS_MHROW;
-                vl.dst = WS_P4OFF + jj * 8; vl.dstride = WS_P4 * 4;
+                srcA = WS_MHOFF + ca * 4; srcB = WS_MHOFF + cb * 4;
+                dst = WS_P4OFF + jj * 8; dstride = WS_P4 * 4;
             }
             float2 win[WS_WIN];
 #define WS_CONSUME_CHUNK(WIN_INDEX)                                                                                              \
     {                                                                                                                            \
         const unsigned s_ = nM % WS_NM;                                                                                          \
-        wait(bars + 8 * (B_FULLM + s_), (nM / WS_NM) & 1);                                                                       \
+        WS_PROF(0)                                                                                                               \
+        mbar_wait(bars + 8 * (B_FULLM + s_), (nM / WS_NM) & 1);                                                                  \
+        WS_PROF(1)                                                                                                               \
         const unsigned base_ = smem + WS_OFF_M + s_ * WS_MCHUNK;                                                                 \
-        _Pragma("unroll") for (int r = 0; r < WS_G; r++)                                                                         \
-            win[WIN_INDEX] = make_float2(lds32(base_ + r * vl.rstride + vl.srcA), lds32(base_ + r * vl.rstride + vl.srcB));      \
+        if (pairlane) {                                                                                                          \
+            _Pragma("unroll") for (int r = 0; r < WS_G; r++) win[WIN_INDEX] = lds64(base_ + r * WS_MPROW + srcA);                \
+        } else {                                                                                                                 \
+            _Pragma("unroll") for (int r = 0; r < WS_G; r++)                                                                     \
+                win[WIN_INDEX] = make_float2(lds32(base_ + r * WS_MHROW + srcA), lds32(base_ + r * WS_MHROW + srcB));            \
+        }                                                                                                                        \
         __syncwarp();                                                                                                            \
         if (lane == 0) mbar_arrive(bars + 8 * (B_EMPTYM + s_));                                                                  \
         nM++;                                                                                                                    \
+        WS_PROF(2)                                                                                                               \
     }
             // the first four chunks of the unit; every group then pulls one more into the last 8 window rows and, when it is
             // done, moves the window down by 8 rows.  (The moves cost 64 register copies per step on the otherwise idle ALU
@@ -456,53 +479,56 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
             for (int c = 0; c < 4; c++) WS_CONSUME_CHUNK(8 * c + r)
 #pragma unroll 1
             for (int g = 0; g < U.ng; g++) {
-                pump();
                 const unsigned ps = nP % WS_NP;
                 WS_CONSUME_CHUNK(32 + r)
-                wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
-                v_compute<FMA>(win, smem + WS_OFF_P + ps * WS_PSLOT, vl, t);
+                mbar_wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
+                WS_PROF(3)
+                const unsigned pd = smem + WS_OFF_P + ps * WS_PSLOT + dst;
+                if (!WS_DBG(1)) v_compute<FMA>(win, pd, dstride, t, active);
+                else if (active)
+                    for (int o = 0; o < WS_G; o++) sts64(pd + o * dstride, win[o + WS_MR]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + 8 * (B_FULLP + ps));
                 nP++;
+                WS_PROF(4)
 #pragma unroll
                 for (int r = 0; r < WS_WIN - WS_G; r++) win[r] = win[r + WS_G];
             }
 #undef WS_CONSUME_CHUNK
         }
-        if (r_prod) { // the R streams feed the U steps that run after the last V group
-            unsigned it = 0;
-            while (rs.u0 < a.nunits || rs.u1 < a.nunits) {
-                pump();
-                __nanosleep(128);
-                if (++it > (1u << 24)) __trap();
-            }
-        }
+        WS_PROF_DUMP
         return;
     }
 
-    // ================= H + solve + U warps =================
+    // ================= H + solve + U warps: two teams of four warps, alternate groups =================
     {
-        const int hw = warp - WS_NVW, ht = tid - WS_NVW * 32;
-        const int hrow = lane & 7, cbase = 16 * hw + 4 * (lane >> 3);   // H: lane = (row, 4-pixel quad)
-        const int urow0 = 4 * (hw & 1), ucol = 32 * (hw >> 1) + lane;   // U: warp = 4 rows x 32 columns
-        unsigned nP = 0, nR0 = 0, nR1 = 0;
+        const int hw = warp - WS_NVW, team = hw >> 2, tw_ = hw & 3, tt = tid - (WS_NVW + WS_TEAMW * team) * 32;
+        const int hrow = lane & 7, cbase = 16 * tw_ + 4 * (lane >> 3);    // H: lane = (row, 4-pixel quad)
+        const int urow0 = 4 * (tw_ >> 1), ucol = 32 * (tw_ & 1) + lane;   // U: warp = 4 rows x 32 columns
+        unsigned n = 0, nR1 = 0; // groups / R1 chunks of the CTA's unit sequence so far
+        WS_PROF_DECL
         for (int u = blockIdx.x; u < a.nunits; u += gridDim.x) {
             const Unit U = decode_unit(a, u);
             const unsigned r1base = nR1;
-            const bool h_active = U.x0 + 16 * hw < w;        // warp-uniform: ragged last strip
-            const bool u_active = U.x0 + 32 * (hw >> 1) < w;
-            for (int g = 0; g < U.ng; g++) {
+            const bool h_active = U.x0 + 16 * tw_ < w;        // warp-uniform: ragged last strip
+            const bool u_active = U.x0 + 32 * (tw_ & 1) < w;
+            for (int g = 0; g < U.ng; g++, n++) {
+                if ((int)(n & 1) != team) continue;
                 const int yg = U.y0 + WS_G * g;
-                const unsigned ps = nP % WS_NP;
-                float *Fb = reinterpret_cast<float *>(ws_smem + WS_OFF_F + (nP & 1) * WS_FSLOT);
-                mbar_wait(bars + 8 * (B_FULLP + ps), (nP / WS_NP) & 1);
+                const unsigned ps = n % WS_NP;
+                float *Fb = reinterpret_cast<float *>(ws_smem + WS_OFF_F + (2 * team + ((n >> 1) & 1)) * WS_FSLOT);
+                WS_PROF(0)
+                mbar_wait(bars + 8 * (B_FULLP + ps), (n / WS_NP) & 1);
+                WS_PROF(1)
                 if (h_active) {
-                    const unsigned char *P = ws_smem + WS_OFF_P + ps * WS_PSLOT;
-                    const float2 *p01 = reinterpret_cast<const float2 *>(P) + hrow * WS_P2 + cbase;
-                    const float2 *p23 = reinterpret_cast<const float2 *>(P + WS_P23OFF) + hrow * WS_P2 + cbase;
-                    const float *p4 = reinterpret_cast<const float *>(P + WS_P4OFF) + hrow * WS_P4 + cbase;
-                    float fx[4], fy[4];
-                    h_quad<FMA>(p01, p23, p4, t, fx, fy);
+                    float fx[4] = {0.25f, 0.25f, 0.25f, 0.25f}, fy[4] = {-0.25f, -0.25f, -0.25f, -0.25f};
+                    if (!WS_DBG(2)) {
+                        const unsigned char *P = ws_smem + WS_OFF_P + ps * WS_PSLOT;
+                        const float2 *p01 = reinterpret_cast<const float2 *>(P) + hrow * WS_P2 + cbase;
+                        const float2 *p23 = reinterpret_cast<const float2 *>(P + WS_P23OFF) + hrow * WS_P2 + cbase;
+                        const float *p4 = reinterpret_cast<const float *>(P + WS_P4OFF) + hrow * WS_P4 + cbase;
+                        h_quad<FMA>(p01, p23, p4, t, fx, fy);
+                    }
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
                         Fb[hrow * WS_FP + cbase + p] = fx[p];
@@ -511,12 +537,14 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + 8 * (B_EMPTYP + ps));
-                nP++;
-                hu_barrier(); // the flow tile of this group is complete; every warp has finished U of the previous group
+                WS_PROF(2)
+                team_barrier(team);
+                WS_PROF(3) // the team's flow tile of this group is complete (the tile is double-buffered: a warp may
+                                    // still read the previous one)
                 if (LAST) {
                     float *f = a.flow + (size_t)U.b * 2 * plane;
 #pragma unroll
-                    for (int i = ht; i < WS_G * WS_SW; i += WS_HU_THREADS) {
+                    for (int i = tt; i < WS_G * WS_SW; i += WS_TEAM_THREADS) {
                         const int row = i / WS_SW, col = i - row * WS_SW;
                         const int x = U.x0 + col, y = yg + row;
                         if (x < w && y < h) {
@@ -529,7 +557,7 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                         const int sx0 = (U.x0 + a.span - 1) / a.span, sy0 = (yg + a.span - 1) / a.span;
                         const int nsx = max(0, (min(U.x0 + WS_SW, w) - 1) / a.span - sx0 + 1), nsy = max(0, (min(yg + WS_G, h) - 1) / a.span - sy0 + 1);
                         int hit = 0;
-                        for (int i = ht; i < nsx * nsy; i += WS_HU_THREADS) {
+                        for (int i = tt; i < nsx * nsy; i += WS_TEAM_THREADS) {
                             const int j = i / nsx, col = (sx0 + i - j * nsx) * a.span - U.x0, row = (sy0 + j) * a.span - yg;
                             const float dx = Fb[row * WS_FP + col], dy = Fb[(WS_G + row) * WS_FP + col];
                             const float len = (dx * dx) + (dy * dy);
@@ -544,24 +572,23 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                     continue;
                 }
                 // ---- U: next update matrices (A.4) from the staged R0 / R1 ----
-                const unsigned rs = nR0 % WS_NR0;
-                mbar_wait(bars + 8 * (B_FULLR0 + rs), (nR0 / WS_NR0) & 1);
-                if (g == 0) {
-                    mbar_wait(bars + 8 * (B_FULLR1 + (r1base % WS_NR1)), (r1base / WS_NR1) & 1);
-                    mbar_wait(bars + 8 * (B_FULLR1 + ((r1base + 1) % WS_NR1)), ((r1base + 1) / WS_NR1) & 1);
+                const unsigned rs = n % WS_NR0;
+                mbar_wait(bars + 8 * (B_FULLR0 + rs), (n / WS_NR0) & 1);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { // the chunks with the rows yg - 8 .. yg + 15
+                    const unsigned nc = r1base + g + k;
+                    mbar_wait(bars + 8 * (B_FULLR1 + nc % WS_NR1), (nc / WS_NR1) & 1);
                 }
-                {
-                    const unsigned n = r1base + g + 2;
-                    mbar_wait(bars + 8 * (B_FULLR1 + (n % WS_NR1)), (n / WS_NR1) & 1);
-                }
-                if (u_active) {
-                    const float *R0s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R0 + rs * WS_R0SLOT) + urow0 * 5 * WS_SW + ucol; // [8][5][96]
-                    const float *R1s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R1);                                             // [32][5][104]
+                WS_PROF(4)
+                if (u_active && !WS_DBG(8)) {
+                    const float *R0s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R0 + rs * WS_R0SLOT) + urow0 * 5 * WS_SW + ucol; // [8][5][64]
+                    const float *R1s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R1);                                             // [48][5][72]
                     const float *Fu = Fb + urow0 * WS_FP + ucol;
                     float *Mo = a.Mout + (size_t)U.b * 5 * plane;
                     const int x = U.x0 + ucol, y0u = yg + urow0;
                     const int xw = U.x0 - WS_R1X;
-                    const int ring0 = WS_G - U.y0 + WS_G * (int)(r1base % WS_NR1); // ring row of frame row yy = (yy + ring0) & 31
+                    // ring row of frame row yy (yg - 8 <= yy <= yg + 15) = (yy - (yg - 8) + rr0) mod 48, rr0 = first ring row of chunk g
+                    const int rr0 = WS_G * (int)((r1base + g) % WS_NR1) - (yg - WS_G);
                     // positions of the thread's four vertically adjacent pixels
                     float dxs[4], dys[4], fxr[4], fyr[4];
                     int x1s[4], y1s[4];
@@ -580,8 +607,9 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
 #pragma unroll
                         for (int pr = 0; pr < 4; pr += 2) { // pixels (pr, pr + 1) packed
                             float2 q[5], pt[5][2], pb[5][2], m[5];
-                            const int ria = (y1s[pr] + ring0) & (WS_NR1 * WS_G - 1), rja = (ria + 1) & (WS_NR1 * WS_G - 1);
-                            const int rib = (y1s[pr + 1] + ring0) & (WS_NR1 * WS_G - 1), rjb = (rib + 1) & (WS_NR1 * WS_G - 1);
+                            int ria = y1s[pr] + rr0, rib = y1s[pr + 1] + rr0;
+                            ria -= ria >= WS_R1RING ? WS_R1RING : 0; rib -= rib >= WS_R1RING ? WS_R1RING : 0;
+                            const int rja = ria + 1 == WS_R1RING ? 0 : ria + 1, rjb = rib + 1 == WS_R1RING ? 0 : rib + 1;
                             const float *a0 = R1s + ria * WS_R1ROW + (x1s[pr] - xw), *a1 = R1s + rja * WS_R1ROW + (x1s[pr] - xw);
                             const float *b0 = R1s + rib * WS_R1ROW + (x1s[pr + 1] - xw), *b1 = R1s + rjb * WS_R1ROW + (x1s[pr + 1] - xw);
 #pragma unroll
@@ -612,7 +640,9 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                             for (int c = 0; c < 5; c++) q[c] = R0s[(q4 * 5 + c) * WS_SW];
                             if (inside) {
                                 if ((unsigned)(x1 - xw) <= (unsigned)(WS_R1C - 2) && (unsigned)(y1 - yg + WS_G) <= (unsigned)(3 * WS_G - 2)) {
-                                    const int ri = (y1 + ring0) & (WS_NR1 * WS_G - 1), rj = (ri + 1) & (WS_NR1 * WS_G - 1);
+                                    int ri = y1 + rr0;
+                                    ri -= ri >= WS_R1RING ? WS_R1RING : 0;
+                                    const int rj = ri + 1 == WS_R1RING ? 0 : ri + 1;
                                     const float *a0 = R1s + ri * WS_R1ROW + (x1 - xw), *a1 = R1s + rj * WS_R1ROW + (x1 - xw);
 #pragma unroll
                                     for (int c = 0; c < 5; c++) {
@@ -635,20 +665,27 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                     }
                 }
                 __syncwarp();
+                WS_PROF(5)
                 if (lane == 0) {
+                    // release.  Chunk c = g + k is read by the groups c - 2 .. c of the unit, i.e. by both teams; each team arrives
+                    // (once per warp) after ITS last use of the chunk, twice where the other team has no group that reads it.
                     mbar_arrive(bars + 8 * (B_EMPTYR0 + rs));
-                    mbar_arrive(bars + 8 * (B_EMPTYR1 + ((r1base + g) % WS_NR1)));
+                    const unsigned e0 = bars + 8 * (B_EMPTYR1 + (r1base + g) % WS_NR1), e1 = bars + 8 * (B_EMPTYR1 + (r1base + g + 1) % WS_NR1);
+                    mbar_arrive(e0);
+                    if (g == 0) mbar_arrive(e0);
+                    mbar_arrive(e1);
+                    if (g == 0 && g + 1 >= U.ng) mbar_arrive(e1);
+                    if (g + 2 >= U.ng) {
+                        const unsigned e2 = bars + 8 * (B_EMPTYR1 + (r1base + g + 2) % WS_NR1);
+                        mbar_arrive(e2);
+                        if (g + 1 >= U.ng) mbar_arrive(e2);
+                    }
                 }
-                nR0++;
+                WS_PROF(6)
             }
-            if (!LAST) { // the two chunks below the last group were staged for its gathers only
-                if (lane == 0) {
-                    mbar_arrive(bars + 8 * (B_EMPTYR1 + ((r1base + U.ng) % WS_NR1)));
-                    mbar_arrive(bars + 8 * (B_EMPTYR1 + ((r1base + U.ng + 1) % WS_NR1)));
-                }
-                nR1 = r1base + U.ng + 2;
-            }
+            nR1 = r1base + U.ng + 2;
         }
+        WS_PROF_DUMP
     }
 }
 
@@ -712,8 +749,8 @@ cudaError_t launch_strip(cudaStream_t s, const StripMaps &m, const StripArgs &sa
 
 static_assert(sizeof(CUtensorMap) * 6 <= sizeof(StripMaps::opaque), "StripMaps holds six tensor maps");
 
-// Tensor maps of one (M buffer, R buffer) pair at one scale: M as [B][h][5*pitch] floats (boxes 256 x {1, 8} and 128 x {1, 8}: rows
-// of a channel-pair plane / of the h2 plane), R as [2B][5h][pitch] floats (boxes 96 x 40 and 104 x 40: 8 rows x 5 channels).
+// Tensor maps of one (M buffer, R buffer) pair at one scale: M as [B][h][5*pitch] floats (boxes 192 x {1, 8} and 96 x {1, 8}: rows
+// of a channel-pair plane / of the h2 plane), R as [2B][5h][pitch] floats (boxes 64 x 40 and 72 x 40: 8 rows x 5 channels).
 bool make_strip_maps(const float *M, const float *R, const LevelDims &d, int batch, StripMaps *out)
 {
     CUtensorMap *maps = reinterpret_cast<CUtensorMap *>(out->opaque);
@@ -741,17 +778,52 @@ cudaError_t launch_gauss_strip(cudaStream_t s, const IterArgs &a, const WinTaps 
     StripArgs sa{};
     sa.R = a.R; sa.Mout = a.Mout; sa.flow = a.flow; sa.d = a.d;
     sa.span = a.last ? a.span : 0; sa.thr2 = a.thr2; sa.counts = a.counts;
+#ifdef TW_STRIP_DEBUG
+    if (const char *e = getenv("TW_STRIP_DBG")) sa.dbg = atoi(e);
+    static unsigned *prof_dev = nullptr;
+    const bool prof = getenv("TW_STRIP_PROF") && !a.last && a.d.w >= 1920;
+    if (prof && !prof_dev) cudaMalloc(&prof_dev, 148 * 16 * 8 * 4);
+    sa.prof = prof ? prof_dev : nullptr;
+#endif
     const int sms = sm_count();
     sa.nsx = (a.d.w + WS_SW - 1) / WS_SW;
-    // vertical segments: about 8 units per SM (tail of the last round), at least 64 rows each (the 40-row window refill of a unit)
+    // vertical segments per strip: the split that minimises (rounds of units over the SMs) x (rows per unit + the cost of a unit's
+    // window refill, about one group); a segment is at least 64 rows
     const int per = a.batch * sa.nsx;
-    int nsy = (8 * sms + per - 1) / per;
-    nsy = std::max(1, std::min(nsy, a.d.h / 64));
-    sa.segh = ((a.d.h + nsy - 1) / nsy + WS_G - 1) & ~(WS_G - 1);
+    int best_nsy = 1;
+    long best_cost = -1;
+    for (int n = 1; n <= std::max(1, std::min(a.d.h / 64, 32)); n++) {
+        const int segh = ((a.d.h + n - 1) / n + WS_G - 1) & ~(WS_G - 1);
+        const int nsy = (a.d.h + segh - 1) / segh;
+        const long rounds = ((long)per * nsy + sms - 1) / sms;
+        const long cost = rounds * (segh + WS_G);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nsy = n; }
+    }
+    sa.segh = ((a.d.h + best_nsy - 1) / best_nsy + WS_G - 1) & ~(WS_G - 1);
     sa.nsy = (a.d.h + sa.segh - 1) / sa.segh;
     sa.nunits = per * sa.nsy;
     const int grid = std::min(sa.nunits, sms);
     if (a.last) return a.fma == 2 ? launch_strip<2, true>(s, m, sa, t, grid) : launch_strip<0, true>(s, m, sa, t, grid);
+#ifdef TW_STRIP_DEBUG
+    if (sa.prof) { // per-role phase clocks of one level-0 launch, averaged over the CTAs
+        cudaError_t e = a.fma == 2 ? launch_strip<2, false>(s, m, sa, t, grid) : launch_strip<0, false>(s, m, sa, t, grid);
+        static int printed = 0;
+        if (e == cudaSuccess && printed++ == 6) {
+            static unsigned hostp[148 * 16 * 8];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(hostp, sa.prof, sizeof(hostp), cudaMemcpyDeviceToHost);
+            for (int wp = 0; wp < 16; wp++) {
+                double acc[8] = {};
+                for (int b = 0; b < grid; b++)
+                    for (int i = 0; i < 8; i++) acc[i] += hostp[(b * 16 + wp) * 8 + i];
+                fprintf(stderr, "strip prof warp %2d:", wp);
+                for (int i = 0; i < 8; i++) fprintf(stderr, " %9.0f", acc[i] / grid);
+                fprintf(stderr, "\n");
+            }
+        }
+        return e;
+    }
+#endif
     return a.fma == 2 ? launch_strip<2, false>(s, m, sa, t, grid) : launch_strip<0, false>(s, m, sa, t, grid);
 }
 
