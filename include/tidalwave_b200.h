@@ -148,9 +148,10 @@ const char *tw_last_error(tw_ctx *ctx);
  *   "gauss_fma"  = 1: symmetric fmaf in the Gaussian window tap sums on top of the faithful arithmetic (oracle relax bit 0).
  *   "update_fma" = 1: fmaf chains in the update matrices on top of "arithmetic" = 1 (oracle relax bit 6; studied, rejected
  *                     as a default: 0.157 px on the reference's scenario1 fixture).
- *   "window_tiles" = 0 / 1: the Gaussian window iterations of radius 15 run the persistent warp-specialised strip kernel
- *                     (tw_window.cu: TMA-fed rings, register-resident column walkers) / the tile-per-CTA kernel.  Same
- *                     arithmetic, bit-identical results; TW_WINDOW=strip|tiles in the environment sets the default.
+ *   "window_tiles" = 0 / 1 / 2: the Gaussian window iterations of radius 15 run the persistent warp-specialised strip kernel
+ *                     (tw_window.cu: TMA tensor-map rings, register-resident column walkers) / the tile-per-CTA kernel / (2, the
+ *                     default) the strip kernel under the relaxed arithmetic and the tile kernel under the faithful one.  Same
+ *                     arithmetic either way, bit-identical results; TW_WINDOW=strip|tiles|auto in the environment sets the default.
  *   "gauss_scalar", "level_generic", "level_unfused", "tight_pitch": alternative code paths kept for the parity tests. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);
 /* Process-wide default of "arithmetic" for contexts created afterwards (the dispatcher's consumers included). */

@@ -2039,6 +2039,179 @@ cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Box window, fused form (window radius m <= 16): no V round trip through HBM.
+//   box_ckpt : the vertical running sums again, but only their state at the top of every 32-row band is kept
+//              (CK[b][band][5 * pitch] doubles, 1.25 B / px instead of 40).
+//   box_band : one CTA = (pair, 32-row band), sweeping the band left to right in 32-column chunks:
+//                (i)   threads = (column, channel) of the chunk + its m + 1 / m halo columns: restart the vertical running sum
+//                      at the band's checkpoint and run it down the 32 rows -- the same additions in the same order as the
+//                      full-column scan, so V is bit-identical -- into shared memory (doubles);
+//                (ii)  threads = (row, channel): the horizontal running sum g += V[x+m] - V[x-m-1] continues across the chunks
+//                      in a register; b = g / winSize^2 -> shared memory (doubles);
+//                (iii) threads = pixels: 2x2 solve (double), then the next update matrices (A.4) from R0 / R1 (coalesced rows,
+//                      bilinear gather) -> M', or on the last iteration the flow store.
+//              Every running sum is evaluated in the oracle's order (App. A.6); nothing is re-associated.
+// ------------------------------------------------------------------------------------------------
+constexpr int BX_BH = 32, BX_CW = 32, BX_THREADS = 256, BX_MAXM = 16;
+__host__ __device__ constexpr int bx_vpitch(int nv) { return ((5 * nv + 10) / 16) * 16 + 5; } // doubles; = 5 mod 16, >= 5 * nv
+constexpr int BX_BPITCH = 165;                                                              // doubles per row of the b tile (= 5 mod 16)
+
+// offset of plane group pg (0: channels 0,1 interleaved; 1: channels 2,3; 2: channel 4) element i in a 5 * pitch M row
+__device__ __forceinline__ int bx_off(int pitch, int pg, int i) { return pg * 2 * pitch + i; }
+
+__global__ void __launch_bounds__(128) box_ckpt_kernel(const float *__restrict__ Min, double *__restrict__ CK, LevelDims d, int m, int nb)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, w = d.w, h = d.h;
+    if (j >= 5 * w) return;
+    const int off = j < 2 * w ? j : j < 4 * w ? 2 * d.pitch + (j - 2 * w) : 4 * d.pitch + (j - 4 * w);
+    const size_t rs = (size_t)5 * d.pitch;
+    const float *M = Min + (size_t)blockIdx.y * 5 * d.plane + off;
+    double *ck = CK + (size_t)blockIdx.y * nb * rs + off;
+    double vs = (double)(M[0] * (float)(m + 2));
+    for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * rs];
+    for (int y0 = 0; y0 < h; y0 += BX_BH) {
+        ck[(size_t)(y0 / BX_BH) * rs] = vs;
+#pragma unroll
+        for (int q = 0; q < BX_BH; q += 16) {
+            float diff[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int y = y0 + q + k;
+                diff[k] = __ldg(M + (size_t)min(y + m, h - 1) * rs) - __ldg(M + (size_t)max(min(y, h - 1) - m - 1, 0) * rs);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (y0 + q + k < h) vs = vs + (double)diff[k];
+        }
+    }
+}
+
+struct BoxBandArgs {
+    const float *Min;  // [B][5] planes
+    const double *CK;  // [B][nb][5 * pitch]
+    const float *R;    // [B][2][5] planes
+    float *Mout;       // [B][5] planes (not last)
+    float *flow;       // [B][2] planes (last)
+    LevelDims d;
+    int m, nb;
+    double scale;
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(BX_THREADS, 2) box_band_kernel(BoxBandArgs a)
+{
+    extern __shared__ __align__(16) double bx_smem[];
+    const int m = a.m, nv = BX_CW + 2 * m + 1, vp = bx_vpitch(nv);
+    double *Vs = bx_smem, *Bs = bx_smem + BX_BH * vp;
+    const int tid = threadIdx.x, b = blockIdx.y, y0 = blockIdx.x * BX_BH;
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const size_t plane = a.d.plane, rs = (size_t)5 * pitch;
+    const float *Mb = a.Min + (size_t)b * 5 * plane;
+    const double *ck = a.CK + ((size_t)b * a.nb + blockIdx.x) * rs;
+    const float *R0 = a.R + (size_t)b * 10 * plane, *R1 = R0 + 5 * plane;
+    const int hr = tid / 5, hc = tid - hr * 5; // stage (ii): (row, channel) for tid < 160
+    const bool hact = tid < BX_BH * 5 && y0 + hr < h;
+    double g = 0.;
+    for (int x0 = 0; x0 < w; x0 += BX_CW) {
+        // ---- (i) vertical running sums of the chunk's V columns x0 - m - 1 .. x0 + 31 + m (clamped = the replicate border) ----
+        for (int t = tid; t < 5 * nv; t += BX_THREADS) {
+            int pg, i, ci, ch;
+            if (t < 4 * nv) { pg = t >= 2 * nv; i = t - pg * 2 * nv; ci = i >> 1; ch = 2 * pg + (i & 1); }
+            else { pg = 2; ci = t - 4 * nv; ch = 4; i = 0; }
+            const int x = clampi(x0 - m - 1 + ci, 0, w - 1);
+            const int off = pg < 2 ? bx_off(pitch, pg, 2 * x + (i & 1)) : bx_off(pitch, 2, x);
+            const float *M = Mb + off;
+            double vs = ck[off];
+            double *vo = Vs + ci * 5 + ch;
+#pragma unroll
+            for (int q = 0; q < BX_BH; q += 8) {
+                float diff[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int y = min(y0 + q + k, h - 1);
+                    diff[k] = __ldg(M + (size_t)min(y + m, h - 1) * rs) - __ldg(M + (size_t)max(y - m - 1, 0) * rs);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    vs = vs + (double)diff[k];
+                    vo[(q + k) * vp] = vs;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (ii) horizontal running sums, one (row, channel) per thread, continued across the chunks ----
+        if (hact) {
+            const double *V = Vs + hr * vp + hc;
+            if (x0 == 0) { // columns 0 .. m - 1 are entries m + 1 .. 2m of the first chunk
+                double t = V[(m + 1) * 5] * (double)(m + 2);
+                for (int x = 1; x < m; x++) t = t + V[(m + 1 + x) * 5];
+                g = t;
+            }
+            double *Bo = Bs + hr * BX_BPITCH + hc;
+            const int n = min(BX_CW, w - x0);
+            for (int s = 0; s < n; s++) {
+                g = g + (V[(s + 2 * m + 1) * 5] - V[s * 5]);
+                Bo[s * 5] = g * a.scale;
+            }
+        }
+        __syncthreads();
+        // ---- (iii) solve + update matrices / flow store: 4 pixels per thread ----
+        {
+            const int lx = tid & 31, ly = tid >> 5, x = x0 + lx;
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) {
+                const int r = ly + 8 * j, y = y0 + r;
+                if (x >= w || y >= h) continue;
+                const double *bb = Bs + r * BX_BPITCH + lx * 5;
+                float fx, fy;
+                solve2x2d(bb[0], bb[1], bb[2], bb[3], bb[4], fx, fy);
+                if (LAST) {
+                    float *f = a.flow + (size_t)b * 2 * plane + (size_t)y * pitch + x;
+                    f[0] = fx; f[plane] = fy;
+                } else {
+                    float mm[5];
+                    update_matrices_px<false>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
+                    store_M(a.Mout + (size_t)b * 5 * plane, pitch, y, x, mm);
+                }
+            }
+        }
+        // the next chunk's stage (i) only writes Vs; its barrier orders this stage's Bs reads before the next stage (ii)
+    }
+}
+
+bool box_fused_ok(const LevelDims &d, int m) { return m >= 1 && m <= BX_MAXM && d.w >= 1 && d.h >= 1; }
+
+cudaError_t launch_box_ckpt(cudaStream_t s, const float *Min, double *CK, const LevelDims &d, int batch, int m)
+{
+    const int nb = (d.h + BX_BH - 1) / BX_BH;
+    dim3 grid((5 * d.w + 127) / 128, batch);
+    box_ckpt_kernel<<<grid, 128, 0, s>>>(Min, CK, d, m, nb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_box_band(cudaStream_t s, const float *Min, const double *CK, const float *R, float *Mout, float *flow, const LevelDims &d,
+                            int batch, int m, int winSize, int last)
+{
+    static bool configured_dev[kMaxDevices][2] = {};
+    BoxBandArgs a{};
+    a.Min = Min; a.CK = CK; a.R = R; a.Mout = Mout; a.flow = flow; a.d = d; a.m = m; a.nb = (d.h + BX_BH - 1) / BX_BH;
+    a.scale = 1. / ((double)winSize * winSize);
+    const size_t smem = sizeof(double) * (size_t)BX_BH * (bx_vpitch(BX_CW + 2 * m + 1) + BX_BPITCH);
+    const size_t smem_max = sizeof(double) * (size_t)BX_BH * (bx_vpitch(BX_CW + 2 * BX_MAXM + 1) + BX_BPITCH);
+    const int dev = current_device();
+    if (!configured_dev[dev][last ? 1 : 0]) {
+        cudaError_t e = last ? cudaFuncSetAttribute(box_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max)
+                             : cudaFuncSetAttribute(box_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        configured_dev[dev][last ? 1 : 0] = true;
+    }
+    dim3 grid(a.nb, batch);
+    if (last) box_band_kernel<true><<<grid, BX_THREADS, smem, s>>>(a);
+    else box_band_kernel<false><<<grid, BX_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Size-tolerance path of OpticalFlow::calculate (/root/reference/src/opticalflow.cpp:64-68): cv::resize of the
 // 8-bit target to the expected size, INTER_LINEAR in effect.  OpenCV's fixed-point bilinear: 11-bit coefficients,
 // horizontal pass in int, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.

@@ -49,7 +49,12 @@ constexpr int WS_VC = WS_SW + 2 * WS_XH;  // 96 V columns
 constexpr int WS_G = 8;                   // rows per group
 constexpr int WS_MR = 15;
 constexpr int WS_WIN = 40;                // register window rows = 5 chunks
-constexpr int WS_NM = 3, WS_NP = 3, WS_NR0 = 3, WS_NR1 = 6, WS_NF = 4; // WS_NF: 2 teams x 2 slots
+#ifdef WS_VAR_NR0_4
+constexpr int WS_NR0 = 4;
+#else
+constexpr int WS_NR0 = 3;
+#endif
+constexpr int WS_NM = 3, WS_NP = 3, WS_NR1 = 6, WS_NF = 4; // WS_NF: 2 teams x 2 slots
 constexpr int WS_MPROW = 2 * WS_VC * 4, WS_MHROW = WS_VC * 4;         // bytes per staged row of a channel-pair plane / of the h2 plane
 constexpr int WS_MP1OFF = WS_G * WS_MPROW, WS_MHOFF = 2 * WS_MP1OFF;  // chunk layout: pair01[8 rows] | pair23[8 rows] | h2[8 rows]
 constexpr int WS_MCHUNK = WS_MHOFF + WS_G * WS_MHROW;                 // 15360
@@ -112,6 +117,25 @@ __device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity)
 // Waits for the phase with the given parity: try_wait suspends the warp in hardware for a short, implementation-defined time
 // and is simply repeated.  A wait of more than ~2 s means a broken pipeline: trap (the launch fails with an error) instead of
 // hanging the device.
+#ifdef WS_VAR_HINT
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or the hint (ns) expires
+__device__ __forceinline__ unsigned mbar_try_hint(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity), "r"((unsigned)WS_VAR_HINT)
+                 : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    if (mbar_try(bar, parity)) return;
+#pragma unroll 1
+    for (unsigned it = 0; !mbar_try_hint(bar, parity); ++it)
+        if (it > (1u << 26)) __trap();
+}
+#else
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     if (mbar_try(bar, parity)) return;
@@ -119,6 +143,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     for (unsigned it = 0; !mbar_try(bar, parity); ++it)
         if (it > (1u << 26)) __trap();
 }
+#endif
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int x, int y, int z, unsigned bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -480,8 +505,14 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
 #pragma unroll 1
             for (int g = 0; g < U.ng; g++) {
                 const unsigned ps = nP % WS_NP;
+#ifdef WS_VAR_EARLYP
+                const unsigned pfree = mbar_try(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1); // probed early: its latency overlaps the chunk loads
+                WS_CONSUME_CHUNK(32 + r)
+                if (!pfree) mbar_wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
+#else
                 WS_CONSUME_CHUNK(32 + r)
                 mbar_wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
+#endif
                 WS_PROF(3)
                 const unsigned pd = smem + WS_OFF_P + ps * WS_PSLOT + dst;
                 if (!WS_DBG(1)) v_compute<FMA>(win, pd, dstride, t, active);
@@ -573,12 +604,25 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                 }
                 // ---- U: next update matrices (A.4) from the staged R0 / R1 ----
                 const unsigned rs = n % WS_NR0;
+#ifdef WS_VAR_RPROBE
+                { // the R0 tile and the chunks with the rows yg - 8 .. yg + 15 (this team waited for chunk g two groups ago): all probes
+                  // are issued before the first result is looked at
+                    const unsigned n1 = r1base + g + 1, n2 = n1 + 1, n0 = n1 - 1;
+                    const unsigned b0 = bars + 8 * (B_FULLR0 + rs), b1 = bars + 8 * (B_FULLR1 + n1 % WS_NR1), b2 = bars + 8 * (B_FULLR1 + n2 % WS_NR1);
+                    const unsigned d0 = mbar_try(b0, (n / WS_NR0) & 1), d1 = mbar_try(b1, (n1 / WS_NR1) & 1), d2 = mbar_try(b2, (n2 / WS_NR1) & 1);
+                    if (g < 2) mbar_wait(bars + 8 * (B_FULLR1 + n0 % WS_NR1), (n0 / WS_NR1) & 1);
+                    if (!d0) mbar_wait(b0, (n / WS_NR0) & 1);
+                    if (!d1) mbar_wait(b1, (n1 / WS_NR1) & 1);
+                    if (!d2) mbar_wait(b2, (n2 / WS_NR1) & 1);
+                }
+#else
                 mbar_wait(bars + 8 * (B_FULLR0 + rs), (n / WS_NR0) & 1);
 #pragma unroll
                 for (int k = 0; k < 3; k++) { // the chunks with the rows yg - 8 .. yg + 15
                     const unsigned nc = r1base + g + k;
                     mbar_wait(bars + 8 * (B_FULLR1 + nc % WS_NR1), (nc / WS_NR1) & 1);
                 }
+#endif
                 WS_PROF(4)
                 if (u_active && !WS_DBG(8)) {
                     const float *R0s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R0 + rs * WS_R0SLOT) + urow0 * 5 * WS_SW + ucol; // [8][5][64]
@@ -612,12 +656,26 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                             const int rja = ria + 1 == WS_R1RING ? 0 : ria + 1, rjb = rib + 1 == WS_R1RING ? 0 : rib + 1;
                             const float *a0 = R1s + ria * WS_R1ROW + (x1s[pr] - xw), *a1 = R1s + rja * WS_R1ROW + (x1s[pr] - xw);
                             const float *b0 = R1s + rib * WS_R1ROW + (x1s[pr + 1] - xw), *b1 = R1s + rjb * WS_R1ROW + (x1s[pr + 1] - xw);
+#ifdef WS_VAR_SHARE
+                            // smooth flow: the lower pixel's top row is the upper pixel's bottom row (same values, 30 loads instead of 40)
+                            const bool share = __all_sync(0xffffffffu, x1s[pr] == x1s[pr + 1] && y1s[pr + 1] == y1s[pr] + 1);
+#pragma unroll
+                            for (int c = 0; c < 5; c++) {
+                                q[c] = make_float2(R0s[(pr * 5 + c) * WS_SW], R0s[((pr + 1) * 5 + c) * WS_SW]);
+                                const float a00 = a0[c * WS_R1C], a01 = a0[c * WS_R1C + 1], a10 = a1[c * WS_R1C], a11 = a1[c * WS_R1C + 1];
+                                float b00 = a10, b01 = a11;
+                                if (!share) { b00 = b0[c * WS_R1C]; b01 = b0[c * WS_R1C + 1]; }
+                                pt[c][0] = make_float2(a00, b00); pt[c][1] = make_float2(a01, b01);
+                                pb[c][0] = make_float2(a10, b1[c * WS_R1C]); pb[c][1] = make_float2(a11, b1[c * WS_R1C + 1]);
+                            }
+#else
 #pragma unroll
                             for (int c = 0; c < 5; c++) {
                                 q[c] = make_float2(R0s[(pr * 5 + c) * WS_SW], R0s[((pr + 1) * 5 + c) * WS_SW]);
                                 pt[c][0] = make_float2(a0[c * WS_R1C], b0[c * WS_R1C]); pt[c][1] = make_float2(a0[c * WS_R1C + 1], b0[c * WS_R1C + 1]);
                                 pb[c][0] = make_float2(a1[c * WS_R1C], b1[c * WS_R1C]); pb[c][1] = make_float2(a1[c * WS_R1C + 1], b1[c * WS_R1C + 1]);
                             }
+#endif
                             upd_core2(q, pt, pb, make_float2(fxr[pr], fxr[pr + 1]), make_float2(fyr[pr], fyr[pr + 1]), make_float2(dxs[pr], dxs[pr + 1]),
                                       make_float2(dys[pr], dys[pr + 1]), t.one, m);
                             const float ma[5] = {m[0].x, m[1].x, m[2].x, m[3].x, m[4].x}, mb[5] = {m[0].y, m[1].y, m[2].y, m[3].y, m[4].y};
