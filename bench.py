@@ -253,7 +253,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e, variants and configs legs (profilers)")
-    ap.add_argument("--pool-consumers", type=int, default=2, help="e2e leg: consumer threads (contexts) per GPU")
+    ap.add_argument("--pool-consumers", type=int, default=1, help="e2e leg: consumer threads (contexts) per GPU")
     ap.add_argument("--e2e-pairs", type=int, default=10000, help="e2e leg: pairs per rank (BASELINE configs[4])")
     ap.add_argument("--arithmetic", default="default", choices=["default", "faithful"],
                     help="default = the library default (relaxed where validated: include/tidalwave_b200.h); faithful = the "

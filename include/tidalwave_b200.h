@@ -116,6 +116,19 @@ int tw_compare_batch(tw_ctx *ctx, int n, const uint8_t *const *expect, const uin
                      int h, int stride, const tw_flow_param *param, double threshold, int span,
                      tw_vector *out, int cap, tw_result *res);
 
+/* ---- pipelined form of tw_compare_batch (what a dispatcher consumer uses: ONE host thread keeps its GPU busy, as the
+ * reference's Consumer does with its device, src/consumer.cpp:18-24, 42-94).  tw_pipe_submit enqueues a batch and returns:
+ * the host -> device copies run on a copy stream through a staging buffer (overlapping the previous batch's kernels), the
+ * compute stream takes them over, runs the launch sequence and snapshots the compact results.  tw_pipe_collect waits for the
+ * OLDEST submitted batch and fills res[0..n) / out exactly as tw_compare_batch does (n = that batch's size).  At most two batches
+ * are in flight (tw_pipe_pending); the images of a submitted batch must stay valid until it has been collected; a change of
+ * size or parameters needs an empty pipe (TW_BAD_PARAMETER otherwise).  Not to be interleaved with the synchronous entry
+ * points while batches are pending. */
+int tw_pipe_submit(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride,
+                   const tw_flow_param *param, double threshold, int span);
+int tw_pipe_collect(tw_ctx *ctx, tw_vector *out, int cap, tw_result *res);
+int tw_pipe_pending(tw_ctx *ctx);
+
 /* ---- split phases of tw_compare_batch (same stream; used by the dispatcher to overlap, and by the
  * benchmark to time the device-resident pass separately from the PCIe legs) ---- */
 int tw_batch_upload(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w,

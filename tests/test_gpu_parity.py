@@ -358,3 +358,46 @@ def test_strip_window_kernel_bit_identical(tw, oracle, size, seed, batch):
             status, vec = oracle.sample(ref[bits], 10, 0.5)
             assert res[0]["status"] == status and _vec_pos(res[0]) == [(v[0], v[1]) for v in vec]
     o.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_batches_match_synchronous(tw):
+    """tw_pipe_submit / tw_pipe_collect (two batches in flight: upload of k + 1 overlaps the kernels of k, results of k - 1 are read
+    from a device snapshot) return exactly what tw_compare_batch returns, in submission order, across a change of batch size."""
+    import ctypes as C
+    lib = tw.load()
+    w, h, B = 640, 360, 3
+    batches = [[tw.synth.make_pair("S" if (i + j) % 2 else "T", w, h, 10 * i + j, defect=(j == 1)) for j in range(n)] for i, n in enumerate((3, 2, 3, 1, 3))]
+    o = tw.OpticalFlow(0, w, h, B)
+    o.set_option("sparse_last", 1)
+    want = [o.calculate_batch(b, threshold=0.4) for b in batches]
+    assert any(r["status"] == "SUSPICIOUS" for rs in want for r in rs)
+    p = tw.OpticalFlowParameter().c()
+    cap = ((w + 9) // 10) * ((h + 9) // 10)
+    vec = (tw.tw_vector * (cap * B))()
+    res = (tw.tw_result * B)()
+    keep, got, pending = [], [], []
+
+    def collect():
+        n = pending.pop(0)
+        assert lib.tw_pipe_collect(o.ctx, vec, cap, res) == 0, o.last_error()
+        got.append([(res[i].status, res[i].n_vectors, [(vec[i * cap + k].x, vec[i * cap + k].y, vec[i * cap + k].dx, vec[i * cap + k].dy)
+                                                       for k in range(min(res[i].n_vectors, cap))]) for i in range(n)])
+    for b in batches:
+        n = len(b)
+        ex = (C.c_void_p * n)(*[x.ctypes.data for x, _ in b]); tg = (C.c_void_p * n)(*[y.ctypes.data for _, y in b])
+        keep.append((b, ex, tg))
+        if lib.tw_pipe_pending(o.ctx) == 2:
+            collect()
+        assert lib.tw_pipe_submit(o.ctx, n, ex, tg, w, h, w, C.byref(p), 0.4, 10) == 0, o.last_error()
+        pending.append(n)
+    while pending:
+        collect()
+    assert lib.tw_pipe_pending(o.ctx) == 0 and lib.tw_pipe_collect(o.ctx, vec, cap, res) != 0
+    names = {0: "OK", 1: "SUSPICIOUS", 2: "ERROR"}
+    for ws, gs in zip(want, got):
+        assert len(ws) == len(gs)
+        for wr, (st, nv, vs) in zip(ws, gs):
+            assert wr["status"] == names[st] and len(wr["vector"]) == nv
+            assert [(v["x"], v["y"], v["dx"], v["dy"]) for v in wr["vector"]] == vs
+    o.close()

@@ -99,6 +99,24 @@ struct tw_ctx {
     int fam_launches[F_COUNT] = {0};
     double fam_bytes[F_COUNT] = {0};
     long long launches = 0;
+    // pipelined batches (tw_pipe_*): upload of batch k + 1 on `copy` into `stage` while batch k runs on `stream`; the results of
+    // a finished batch are snapshot on the device so that the host reads them (on `fetch`) while the next batch runs
+    struct PipeSlot {
+        cudaEvent_t done = nullptr, r0 = nullptr, r1 = nullptr;
+        int *d_counts = nullptr, *h_counts = nullptr;
+        void *d_vec = nullptr;
+        size_t vec_bytes = 0;
+        int n = 0, w = 0, h = 0, dev_cap = 0;
+    };
+    struct Pipe {
+        cudaStream_t copy = nullptr, fetch = nullptr;
+        uint8_t *stage = nullptr;
+        size_t stage_bytes = 0;
+        cudaEvent_t ev_up = nullptr, ev_stage_free = nullptr;
+        bool stage_used = false;
+        PipeSlot slot[2];
+        int head = 0, count = 0;
+    } pipe;
     void *rs_buf = nullptr; // +-5 px resize path: raw target + coefficient tables
     size_t rs_cap = 0;
     void *flush_buf = nullptr;
@@ -767,6 +785,22 @@ void tw_destroy(tw_ctx *ctx)
     if (ctx->d_vectors) cudaFree(ctx->d_vectors);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->rs_buf) cudaFree(ctx->rs_buf);
+    {
+        tw_ctx::Pipe &pp = ctx->pipe;
+        if (pp.copy) { cudaStreamSynchronize(pp.copy); cudaStreamDestroy(pp.copy); }
+        if (pp.fetch) { cudaStreamSynchronize(pp.fetch); cudaStreamDestroy(pp.fetch); }
+        if (pp.stage) cudaFree(pp.stage);
+        if (pp.ev_up) cudaEventDestroy(pp.ev_up);
+        if (pp.ev_stage_free) cudaEventDestroy(pp.ev_stage_free);
+        for (auto &s : pp.slot) {
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.r0) cudaEventDestroy(s.r0);
+            if (s.r1) cudaEventDestroy(s.r1);
+            if (s.d_counts) cudaFree(s.d_counts);
+            if (s.h_counts) cudaFreeHost(s.h_counts);
+            if (s.d_vec) cudaFree(s.d_vec);
+        }
+    }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->ev_r0) cudaEventDestroy(ctx->ev_r0);
@@ -979,6 +1013,129 @@ int tw_compare_batch(tw_ctx *ctx, int n, const uint8_t *const *expect, const uin
     rc = tw_batch_run(ctx, n, w, h, param, threshold, span);
     if (rc != TW_OK) return fail_all(rc, ctx->err.c_str());
     return tw_batch_fetch(ctx, n, out, cap, res);
+}
+
+// ---- pipelined form of tw_compare_batch: at most two batches in flight per context ----
+// tw_pipe_submit returns as soon as everything is enqueued: the H2D copies of this batch go through a staging buffer on a copy
+// stream (they overlap the previous batch's kernels), the compute stream takes them over with one device copy, runs the
+// launch sequence and snapshots the compact results; tw_pipe_collect waits for the OLDEST batch and reads its snapshot on a third
+// stream while the newer batch keeps running.  One host thread per GPU keeps the device busy this way (the reference: one
+// Consumer thread per GPU, /root/reference/src/consumer.cpp:18-24, 42-94).
+int tw_pipe_pending(tw_ctx *ctx) { return ctx ? ctx->pipe.count : 0; }
+
+int tw_pipe_submit(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride,
+                   const tw_flow_param *param, double threshold, int span)
+{
+    if (!ctx) return TW_BAD_PARAMETER;
+    tw_ctx::Pipe &pp = ctx->pipe;
+    if (pp.count >= 2) { ctx->err = "tw_pipe_submit: two batches in flight, collect one first"; return TW_BAD_PARAMETER; }
+    if (n < 1 || n > ctx->max_batch || w < 1 || h < 1 || stride < w || span < 1) { ctx->err = "bad batch/size/span"; return TW_BAD_PARAMETER; }
+    if ((ctx->max_w > 0 && w > ctx->max_w) || (ctx->max_h > 0 && h > ctx->max_h)) { ctx->err = "image larger than the context's max_w x max_h"; return TW_BAD_PARAMETER; }
+    if (validate_param(param) != TW_OK) { ctx->err = "bad optical-flow parameter"; return TW_BAD_PARAMETER; }
+    for (int i = 0; i < n; i++)
+        if (!expect[i] || !target[i]) { ctx->err = "null image"; return TW_BAD_IMAGE_FORMAT; }
+    cudaSetDevice(ctx->device);
+    const Plan &pl0 = ctx->plan;
+    const bool same_plan = pl0.valid && pl0.W == w && pl0.H == h && pl0.batch == ctx->max_batch && pl0.keep == ctx->keep_levels && same_param(pl0.p, *param);
+    if (!same_plan && pp.count > 0) { ctx->err = "tw_pipe_submit: size / parameters changed, collect the pending batch first"; return TW_BAD_PARAMETER; }
+    if (!build_plan(ctx, w, h, *param)) return TW_CUDA_ERROR;
+    Plan &pl = ctx->plan;
+    cudaError_t e = cudaSuccess;
+    if (!pp.copy) {
+        if ((e = cudaStreamCreateWithFlags(&pp.copy, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&pp.fetch, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&pp.ev_up, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&pp.ev_stage_free, cudaEventDisableTiming)) != cudaSuccess) { set_err(ctx, "pipe setup", e); return TW_CUDA_ERROR; }
+        for (auto &s : pp.slot) {
+            if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreate(&s.r0)) != cudaSuccess ||
+                (e = cudaEventCreate(&s.r1)) != cudaSuccess || (e = cudaMalloc(&s.d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
+                (e = cudaMallocHost(&s.h_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess) { set_err(ctx, "pipe setup", e); return TW_CUDA_ERROR; }
+        }
+    }
+    const size_t pair_bytes = (size_t)2 * h * pl.spitch, need = (size_t)ctx->max_batch * pair_bytes;
+    if (pp.stage_bytes < need) { // only with nothing in flight (same_plan is false for a new size)
+        cudaStreamSynchronize(pp.copy);
+        cudaStreamSynchronize(ctx->stream);
+        if (pp.stage) cudaFree(pp.stage);
+        pp.stage = nullptr; pp.stage_bytes = 0; pp.stage_used = false;
+        if ((e = cudaMalloc(&pp.stage, need)) != cudaSuccess) { set_err(ctx, "cudaMalloc stage", e); return TW_CUDA_ERROR; }
+        pp.stage_bytes = need;
+    }
+    // copy stream: the staging buffer is free once the previous batch's take-over copy has run
+    if (pp.stage_used) cudaStreamWaitEvent(pp.copy, pp.ev_stage_free, 0);
+    for (int i = 0; i < n; i++) {
+        uint8_t *d = pp.stage + (size_t)i * pair_bytes;
+        e = cudaMemcpy2DAsync(d, pl.spitch, expect[i], stride, w, h, cudaMemcpyHostToDevice, pp.copy);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(d + (size_t)h * pl.spitch, pl.spitch, target[i], stride, w, h, cudaMemcpyHostToDevice, pp.copy);
+        if (e != cudaSuccess) { set_err(ctx, "H2D", e); return TW_CUDA_ERROR; }
+    }
+    cudaEventRecord(pp.ev_up, pp.copy);
+    // compute stream
+    tw_ctx::PipeSlot &s = pp.slot[(pp.head + pp.count) & 1];
+    cudaStreamWaitEvent(ctx->stream, pp.ev_up, 0);
+    e = cudaMemcpyAsync(pl.src, pp.stage, (size_t)n * pair_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "stage -> src", e); return TW_CUDA_ERROR; }
+    cudaEventRecord(pp.ev_stage_free, ctx->stream);
+    pp.stage_used = true;
+    cudaEventRecord(s.r0, ctx->stream);
+    if (!run_sequence(ctx, n, threshold, span)) return TW_CUDA_ERROR;
+    cudaEventRecord(s.r1, ctx->stream);
+    ctx->last_n = n; ctx->last_w = w; ctx->last_h = h; ctx->ran = true;
+    ctx->last_sparse = sparse_in_effect(ctx, span);
+    // snapshot of the compact results (counts + vectors), then the counts to the host
+    const size_t vbytes = (size_t)n * ctx->dev_cap * sizeof(tw_vector);
+    if (s.vec_bytes < vbytes) {
+        if (s.d_vec) { cudaStreamSynchronize(pp.fetch); cudaFree(s.d_vec); s.d_vec = nullptr; s.vec_bytes = 0; }
+        const size_t full = (size_t)ctx->max_batch * ctx->dev_cap * sizeof(tw_vector);
+        if ((e = cudaMalloc(&s.d_vec, full)) != cudaSuccess) { set_err(ctx, "cudaMalloc snapshot", e); return TW_CUDA_ERROR; }
+        s.vec_bytes = full;
+    }
+    e = cudaMemcpyAsync(s.d_counts, ctx->d_counts, sizeof(int) * n, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_vec, ctx->d_vectors, vbytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) { set_err(ctx, "snapshot", e); return TW_CUDA_ERROR; }
+    cudaEventRecord(s.done, ctx->stream);
+    s.n = n; s.w = w; s.h = h; s.dev_cap = ctx->dev_cap;
+    pp.count++;
+    return TW_OK;
+}
+
+int tw_pipe_collect(tw_ctx *ctx, tw_vector *out, int cap, tw_result *res)
+{
+    if (!ctx || !res) return TW_BAD_PARAMETER;
+    tw_ctx::Pipe &pp = ctx->pipe;
+    if (pp.count < 1) { ctx->err = "tw_pipe_collect: nothing in flight"; return TW_BAD_PARAMETER; }
+    cudaSetDevice(ctx->device);
+    tw_ctx::PipeSlot &s = pp.slot[pp.head];
+    pp.head ^= 1; pp.count--;
+    const int n = s.n;
+    cudaError_t e = cudaEventSynchronize(s.done);
+    if (e != cudaSuccess) {
+        set_err(ctx, "collect", e);
+        for (int i = 0; i < n; i++) fill_error(&res[i], TW_CUDA_ERROR, ctx->err.c_str());
+        return TW_CUDA_ERROR;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s.r0, s.r1);
+    bool copied = false;
+    for (int i = 0; i < n; i++) {
+        const int cnt = s.h_counts[i];
+        memset(&res[i], 0, sizeof(tw_result));
+        res[i].code = TW_OK;
+        res[i].status = cnt == 0 ? TW_STATUS_OK : TW_STATUS_SUSPICIOUS;
+        res[i].n_vectors = cnt;
+        res[i].width = s.w; res[i].height = s.h;
+        res[i].time = ms * 1e-3f / n;
+        const int ncopy = std::min(std::min(cnt, cap), s.dev_cap);
+        if (ncopy > 0 && out) {
+            e = cudaMemcpyAsync(out + (size_t)i * cap, (const tw_vector *)s.d_vec + (size_t)i * s.dev_cap, sizeof(tw_vector) * ncopy,
+                                cudaMemcpyDeviceToHost, pp.fetch);
+            if (e != cudaSuccess) { set_err(ctx, "collect vectors", e); fill_error(&res[i], TW_CUDA_ERROR, ctx->err.c_str()); }
+            copied = true;
+        }
+    }
+    if (copied && (e = cudaStreamSynchronize(pp.fetch)) != cudaSuccess) { set_err(ctx, "collect sync", e); return TW_CUDA_ERROR; }
+    return TW_OK;
 }
 
 int tw_compare(tw_ctx *ctx, const uint8_t *expect, int ew, int eh, const uint8_t *target, int tw_, int th_,

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -99,24 +100,50 @@ void consumer_main(tw_pool *p, int idx)
     std::vector<tw_result> res(p->batch);
     std::vector<Request> work;
     std::vector<const uint8_t *> ex(p->batch), tg(p->batch);
+    // Up to two batches are in flight on the context (tw_pipe_*): while batch k runs, this thread pops and uploads batch k + 1
+    // and then collects batch k - 1 -- one consumer thread per GPU keeps the device busy (src/consumer.cpp:18-24).
+    struct InFlight { std::vector<Request> work; int cap = 0; };
+    std::deque<InFlight> inflight;
+    auto collect_oldest = [&]() {
+        InFlight f = std::move(inflight.front());
+        inflight.pop_front();
+        const int n = (int)f.work.size();
+        if (vec.size() < (size_t)n * f.cap) vec.resize((size_t)n * f.cap);
+        tw_pipe_collect(ctx, vec.data(), f.cap, res.data());
+        for (int i = 0; i < n; i++) publish(p, f.work[i].id, res[i], vec.data() + (size_t)i * f.cap, std::min(res[i].n_vectors, f.cap));
+        p->cv_res.notify_all();
+    };
     for (;;) {
         work.clear();
         {
-            // MessageQueue::tryPop, src/message_queue.h:67-85: wait for a request or the stop notice
+            // MessageQueue::tryPop, src/message_queue.h:67-85: wait for a request or the stop notice; with batches in flight do
+            // not block -- their results are due
             std::unique_lock<std::mutex> lk(p->mu);
-            p->cv_req.wait(lk, [&] { return !p->queue.empty() || !p->running; });
+            if (inflight.empty()) p->cv_req.wait(lk, [&] { return !p->queue.empty() || !p->running; });
             if (!p->running) break;
-            work.push_back(p->queue.front());
-            p->queue.pop_front();
-            // batch: take the following requests while they are compute-ready and have the same size
-            const Request &h = work[0];
-            bool head_ok = h.expect && h.target && h.ew == h.tw && h.eh == h.th;
-            while (head_ok && (int)work.size() < p->batch && !p->queue.empty()) {
-                const Request &q = p->queue.front();
-                if (!(q.expect && q.target && q.ew == h.ew && q.eh == h.eh && q.tw == h.ew && q.th == h.eh)) break;
-                work.push_back(q);
+            if (!p->queue.empty()) {
+                work.push_back(p->queue.front());
                 p->queue.pop_front();
+                // batch: take the following requests while they are compute-ready and have the same size; while the GPU is
+                // still busy with an earlier batch there is time to let a short queue fill up (bounded: <= 20 x 50 us)
+                const Request h = work[0];
+                const bool head_ok = h.expect && h.target && h.ew == h.tw && h.eh == h.th;
+                for (int spins = 0; head_ok && (int)work.size() < p->batch; ) {
+                    if (p->queue.empty()) {
+                        if (inflight.empty() || spins++ >= 20 || !p->running) break;
+                        p->cv_req.wait_for(lk, std::chrono::microseconds(50));
+                        continue;
+                    }
+                    const Request &q = p->queue.front();
+                    if (!(q.expect && q.target && q.ew == h.ew && q.eh == h.eh && q.tw == h.ew && q.th == h.eh)) break;
+                    work.push_back(q);
+                    p->queue.pop_front();
+                }
             }
+        }
+        if (work.empty()) { // nothing new: deliver the oldest batch in flight
+            collect_oldest();
+            continue;
         }
         if (!ctx) {
             for (auto &r : work) {
@@ -129,21 +156,35 @@ void consumer_main(tw_pool *p, int idx)
         }
         int cap = p->vector_cap;
         if (cap <= 0) cap = std::max(1, ((work[0].ew + p->span - 1) / p->span) * ((work[0].eh + p->span - 1) / p->span));
-        if (vec.size() < work.size() * (size_t)cap) vec.resize(work.size() * (size_t)cap);
-        if (work.size() == 1) {
-            const Request &r = work[0];
-            tw_compare(ctx, r.expect, r.ew, r.eh, r.target, r.tw, r.th, &p->param, p->threshold, p->span, vec.data(), cap, &res[0]);
-            publish(p, r.id, res[0], vec.data(), std::min(res[0].n_vectors, cap));
-        } else {
-            int n = (int)work.size();
-            for (int i = 0; i < n; i++) { ex[i] = work[i].expect; tg[i] = work[i].target; }
-            tw_compare_batch(ctx, n, ex.data(), tg.data(), work[0].ew, work[0].eh, work[0].ew, &p->param, p->threshold, p->span,
-                             vec.data(), cap, res.data());
-            for (int i = 0; i < n; i++)
-                publish(p, work[i].id, res[i], vec.data() + (size_t)i * cap, std::min(res[i].n_vectors, cap));
+        const Request &r0 = work[0];
+        const bool same = r0.expect && r0.target && r0.ew == r0.tw && r0.eh == r0.th;
+        if (!same) {
+            // error cases and the +-5 px resize path of OpticalFlow::calculate (src/opticalflow.cpp:37-68): synchronous, pipe drained
+            while (!inflight.empty()) collect_oldest();
+            if (vec.size() < (size_t)cap) vec.resize(cap);
+            tw_compare(ctx, r0.expect, r0.ew, r0.eh, r0.target, r0.tw, r0.th, &p->param, p->threshold, p->span, vec.data(), cap, &res[0]);
+            publish(p, r0.id, res[0], vec.data(), std::min(res[0].n_vectors, cap));
+            p->cv_res.notify_all();
+            continue;
         }
-        p->cv_res.notify_all();
+        const int n = (int)work.size();
+        for (int i = 0; i < n; i++) { ex[i] = work[i].expect; tg[i] = work[i].target; }
+        if (!inflight.empty() && (inflight.back().work[0].ew != r0.ew || inflight.back().work[0].eh != r0.eh))
+            while (!inflight.empty()) collect_oldest(); // a new size rebuilds the plan: nothing may be in flight
+        if (tw_pipe_pending(ctx) >= 2) collect_oldest();
+        int rc = tw_pipe_submit(ctx, n, ex.data(), tg.data(), r0.ew, r0.eh, r0.ew, &p->param, p->threshold, p->span);
+        if (rc != TW_OK) {
+            tw_result e;
+            fill_error(&e, rc, tw_last_error(ctx));
+            for (auto &r : work) publish(p, r.id, e, nullptr, 0);
+            p->cv_res.notify_all();
+            continue;
+        }
+        InFlight f;
+        f.work = work; f.cap = cap;
+        inflight.push_back(std::move(f));
     }
+    while (ctx && !inflight.empty()) collect_oldest(); // stop: requests already on the device are still answered
     if (ctx) tw_destroy(ctx);
 }
 
