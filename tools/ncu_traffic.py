@@ -20,7 +20,7 @@ for r in rows[1:]:
     n = r[iname]
     if "gauss_last_sparse" in n:
         f = "gauss_last"
-    elif "gauss_iter" in n:
+    elif "gauss_iter" in n or "gauss_strip" in n:
         f = "gauss_last" if g % iters == iters - 1 else "gauss_iter"
         g += 1
     elif "polyexp" in n: f = "polyexp"

@@ -6,13 +6,15 @@ tag=${1:-rXX}; o=gpurun_out
 python -m pytest tests -m gpu -x -q > $o/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_reference.json 2>> $o/${tag}_bench.err; echo "reference rc=$?"
-python bench.py --batch 32 --no-cpu > $o/${tag}_bench_b32.json 2>> $o/${tag}_bench.err; echo "b32 rc=$?"
+python bench.py --batch 32 --no-cpu --e2e-pairs 4000 > $o/${tag}_bench_b32.json 2>> $o/${tag}_bench.err; echo "b32 rc=$?"
 python tools/parity_report.py > $o/${tag}_parity_fullsize.jsonl 2> $o/${tag}_parity.err; echo "parity rc=$?"
 export TW_GRAPH=0
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
 $CMD > $o/${tag}_plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_batch16.csv $CMD > $o/${tag}_ncu_launches.log 2>&1; echo "launch list rc=$?"
-$CMD > $o/${tag}_plain2.log 2>&1 && ncu --set full --clock-control none -k regex:"gauss_iter2|gauss_last_sparse|polyexp|first_update|level_" -s 63 -c 21 -o /tmp/prof_${tag} $CMD > $o/${tag}_ncu_full.log 2>&1; echo "full rc=$?"
+$CMD > $o/${tag}_plain2.log 2>&1 && ncu --set full --clock-control none -k regex:"gauss_strip|gauss_iter2|gauss_last_sparse|polyexp|first_update|level_" -s 63 -c 21 -o /tmp/prof_${tag} $CMD > $o/${tag}_ncu_full.log 2>&1; echo "full rc=$?"
 python tools/ncu_summary.py /tmp/prof_${tag}.ncu-rep $o/${tag}_ncu_full_step_batch16.csv
 python tools/ncu_traffic.py $o/${tag}_ncu_full_step_batch16.csv 16 relaxed > $o/${tag}_traffic.json
-$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_iter2" -s 42 -c 1 -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
+# source-level capture of a level-0 launch of the window kernel (the strip kernel launches 11 times per step; indices 9, 10 are the finest scale)
+$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_strip" -s 20 -c 1 -f -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
+python tools/cfg_bench.py cfg3 > $o/${tag}_cfg3.json 2>> $o/${tag}_bench.err; python tools/cfg_bench.py cfg4 > $o/${tag}_cfg4.json 2>> $o/${tag}_bench.err
 ls -la $o | grep ${tag}
