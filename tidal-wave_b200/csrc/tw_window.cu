@@ -5,9 +5,10 @@
 //   the per-iteration body of cv::calcOpticalFlowFarneback, /root/reference/src/opticalflow.cpp:83-85 -- fused into one
 //   pass: per iteration M (20 B/px), R0 (20), R1 (20) are read once and M' (20) is written once.
 //
-// Roles of the 16 warps of a CTA (one CTA per SM, 128 registers per thread, ~215 KB of shared memory).  Every scheduler of
-// the SM holds two V warps and two H / U warps, so the FFMA2-dense vertical pass and the load / FP64 / address-heavy solve and
-// update passes share each issue port:
+// Roles of the warps of a CTA (one CTA per SM, ~206 KB of shared memory).  The kernel is launched with 20 warps at 96 registers;
+// the four warps of the last warpgroup (the TMA producer and three spares that exit) shrink to 24 registers and the sixteen working
+// warps grow to 112 (setmaxnreg; USETMAXREG in SASS).  Every scheduler of the SM holds two V warps and two H / U warps, so the
+// FFMA2-dense vertical pass and the load / FP64 / address-heavy solve and update passes share each issue port:
 //   warps 0-7    V walkers: thread = (column, channel pair) [warps 0-5] or (column pair, h2) [warps 6-7, 48 lanes].  Each keeps a
 //                40-row sliding window of its column in REGISTERS for the whole strip, so an M row is read from L2 exactly once
 //                per strip and there is no cold start per tile; per 8-row group: 8 new rows from the M ring, 8 outputs x 31
@@ -19,15 +20,23 @@
 //                off the damped frame border), a scalar per-pixel path otherwise (pixels whose displaced position leaves the
 //                staged window -- large motion -- gather from global memory; same values, same arithmetic) -> M' stores;
 //                (last) flow stores + the fused span-grid threshold count.
-//   TMA          tensor-map bulk copies (cp.async.bulk.tensor, UTMALDG) into three rings: the M rows (8-row chunks, one 8-row box
-//                per plane; at the frame top / bottom one row per copy with the row coordinate clamped = the replicate border
-//                of App. A.5), the R0 tile of each group (64 x 8 x 5 channels) and the R1 rows its bilinear gather can touch
-//                (72 columns x rows y-8 .. y+15, a 6-chunk row ring).  There is no producer warp and nobody polls: the LAST
-//                consumer of a ring slot (a shared-memory counter tells which warp that is) issues the copy that refills it,
-//                NM / NR0 / NR1 chunks ahead in the CTA's unit sequence.  Out-of-frame parts are zero-filled by the TMA unit and
-//                never read.
-//   Hand-offs: "full" mbarriers (TMA transaction bytes; V -> H arrivals), an "empty" mbarrier per P slot, the consumer counters
-//   above, and one 128-thread named barrier per team between H and U.  Every wait traps after ~2 s instead of hanging.
+//   warp 16      TMA producer (one lane): tensor-map bulk copies (cp.async.bulk.tensor, UTMALDG) issued as far ahead as the rings
+//                allow -- the M rows (8-row chunks, one 8-row box per plane; at the frame top / bottom one row per copy with the
+//                row coordinate clamped = the replicate border of App. A.5; 3 slots), the R0 tile of each group (64 x 8 x 5
+//                channels; 3 slots) and the R1 rows its bilinear gather can touch (72 columns x rows y-8 .. y+15, a 6-chunk row
+//                ring).  Out-of-frame parts are zero-filled by the TMA unit and never read.  It polls the "empty" barriers
+//                (mbarrier.test_wait) and never blocks on one stream while another could be served.
+//   All hand-offs are mbarrier pipelines (full / empty per ring slot; an R1 chunk is read by three consecutive groups, i.e. by
+//   both teams: each team arrives after its last use of the chunk) plus one 128-thread named barrier per team between H and U.
+//   Every wait traps after ~2 s instead of hanging the device.
+//
+// What was measured on the way: 96-column strips with 10 V + 6 H / U warps and the producers inside two V
+// warps ran 38 % SLOWER than the tile kernel (the H / U warps, 1.5 per scheduler and latency-bound, held the V walkers back, and
+// the producers' polling sat on the V warps' critical path); 64-column strips with a dedicated producer warp at 96 registers and
+// eight software-pipelined H / U warps (2 pixels per lane: too little ILP) 23 % slower; the same with the producer replaced by
+// "the last consumer of a slot refills it" 40 % slower (the refill code and its atomics moved onto the consumers' critical
+// path).  This form equals the tile kernel in the relaxed arithmetic (2.36 vs 2.33 ms per step), is 12 % faster at 3840x2160 and
+// 5 % slower in the faithful arithmetic (three packed instructions per tap pair instead of two).
 //
 // Arithmetic per output is exactly that of gauss_iter2_kernel (tw_kernels.cu): FMA = 0 the oracle's add-mul-add order
 // (bit-identical to oracle/farneback_ref.c), FMA = 2 the direct-form fmaf taps of the relaxed default (oracle relax bit 7).
@@ -49,11 +58,7 @@ constexpr int WS_VC = WS_SW + 2 * WS_XH;  // 96 V columns
 constexpr int WS_G = 8;                   // rows per group
 constexpr int WS_MR = 15;
 constexpr int WS_WIN = 40;                // register window rows = 5 chunks
-#ifdef WS_VAR_NR0_4
-constexpr int WS_NR0 = 4;
-#else
 constexpr int WS_NR0 = 3;
-#endif
 constexpr int WS_NM = 3, WS_NP = 3, WS_NR1 = 6, WS_NF = 4; // WS_NF: 2 teams x 2 slots
 constexpr int WS_MPROW = 2 * WS_VC * 4, WS_MHROW = WS_VC * 4;         // bytes per staged row of a channel-pair plane / of the h2 plane
 constexpr int WS_MP1OFF = WS_G * WS_MPROW, WS_MHOFF = 2 * WS_MP1OFF;  // chunk layout: pair01[8 rows] | pair23[8 rows] | h2[8 rows]
@@ -117,33 +122,11 @@ __device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity)
 // Waits for the phase with the given parity: try_wait suspends the warp in hardware for a short, implementation-defined time
 // and is simply repeated.  A wait of more than ~2 s means a broken pipeline: trap (the launch fails with an error) instead of
 // hanging the device.
-#ifdef WS_VAR_HINT
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or the hint (ns) expires
-__device__ __forceinline__ unsigned mbar_try_hint(unsigned bar, unsigned parity)
-{
-    unsigned done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity), "r"((unsigned)WS_VAR_HINT)
-                 : "memory");
-    return done;
-}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     if (mbar_try(bar, parity)) return;
 #pragma unroll 1
-    for (unsigned it = 0; !mbar_try_hint(bar, parity); ++it)
-        if (it > (1u << 26)) __trap();
-}
-#else
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-    if (mbar_try(bar, parity)) return;
-#pragma unroll 1
-    for (unsigned it = 0; !mbar_try(bar, parity); ++it)
-        if (it > (1u << 26)) __trap();
-}
-#endif
+    for (unsigned it = 0; !mbar_try(bar, parity); ++it) {
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int x, int y, int z, unsigned bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -505,14 +488,8 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
 #pragma unroll 1
             for (int g = 0; g < U.ng; g++) {
                 const unsigned ps = nP % WS_NP;
-#ifdef WS_VAR_EARLYP
-                const unsigned pfree = mbar_try(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1); // probed early: its latency overlaps the chunk loads
-                WS_CONSUME_CHUNK(32 + r)
-                if (!pfree) mbar_wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
-#else
                 WS_CONSUME_CHUNK(32 + r)
                 mbar_wait(bars + 8 * (B_EMPTYP + ps), ((nP / WS_NP) & 1) ^ 1);
-#endif
                 WS_PROF(3)
                 const unsigned pd = smem + WS_OFF_P + ps * WS_PSLOT + dst;
                 if (!WS_DBG(1)) v_compute<FMA>(win, pd, dstride, t, active);
@@ -604,25 +581,12 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                 }
                 // ---- U: next update matrices (A.4) from the staged R0 / R1 ----
                 const unsigned rs = n % WS_NR0;
-#ifdef WS_VAR_RPROBE
-                { // the R0 tile and the chunks with the rows yg - 8 .. yg + 15 (this team waited for chunk g two groups ago): all probes
-                  // are issued before the first result is looked at
-                    const unsigned n1 = r1base + g + 1, n2 = n1 + 1, n0 = n1 - 1;
-                    const unsigned b0 = bars + 8 * (B_FULLR0 + rs), b1 = bars + 8 * (B_FULLR1 + n1 % WS_NR1), b2 = bars + 8 * (B_FULLR1 + n2 % WS_NR1);
-                    const unsigned d0 = mbar_try(b0, (n / WS_NR0) & 1), d1 = mbar_try(b1, (n1 / WS_NR1) & 1), d2 = mbar_try(b2, (n2 / WS_NR1) & 1);
-                    if (g < 2) mbar_wait(bars + 8 * (B_FULLR1 + n0 % WS_NR1), (n0 / WS_NR1) & 1);
-                    if (!d0) mbar_wait(b0, (n / WS_NR0) & 1);
-                    if (!d1) mbar_wait(b1, (n1 / WS_NR1) & 1);
-                    if (!d2) mbar_wait(b2, (n2 / WS_NR1) & 1);
-                }
-#else
                 mbar_wait(bars + 8 * (B_FULLR0 + rs), (n / WS_NR0) & 1);
 #pragma unroll
                 for (int k = 0; k < 3; k++) { // the chunks with the rows yg - 8 .. yg + 15
                     const unsigned nc = r1base + g + k;
                     mbar_wait(bars + 8 * (B_FULLR1 + nc % WS_NR1), (nc / WS_NR1) & 1);
                 }
-#endif
                 WS_PROF(4)
                 if (u_active && !WS_DBG(8)) {
                     const float *R0s = reinterpret_cast<const float *>(ws_smem + WS_OFF_R0 + rs * WS_R0SLOT) + urow0 * 5 * WS_SW + ucol; // [8][5][64]
@@ -656,26 +620,12 @@ gauss_strip_kernel(const __grid_constant__ CUtensorMap mapMp, const __grid_const
                             const int rja = ria + 1 == WS_R1RING ? 0 : ria + 1, rjb = rib + 1 == WS_R1RING ? 0 : rib + 1;
                             const float *a0 = R1s + ria * WS_R1ROW + (x1s[pr] - xw), *a1 = R1s + rja * WS_R1ROW + (x1s[pr] - xw);
                             const float *b0 = R1s + rib * WS_R1ROW + (x1s[pr + 1] - xw), *b1 = R1s + rjb * WS_R1ROW + (x1s[pr + 1] - xw);
-#ifdef WS_VAR_SHARE
-                            // smooth flow: the lower pixel's top row is the upper pixel's bottom row (same values, 30 loads instead of 40)
-                            const bool share = __all_sync(0xffffffffu, x1s[pr] == x1s[pr + 1] && y1s[pr + 1] == y1s[pr] + 1);
-#pragma unroll
-                            for (int c = 0; c < 5; c++) {
-                                q[c] = make_float2(R0s[(pr * 5 + c) * WS_SW], R0s[((pr + 1) * 5 + c) * WS_SW]);
-                                const float a00 = a0[c * WS_R1C], a01 = a0[c * WS_R1C + 1], a10 = a1[c * WS_R1C], a11 = a1[c * WS_R1C + 1];
-                                float b00 = a10, b01 = a11;
-                                if (!share) { b00 = b0[c * WS_R1C]; b01 = b0[c * WS_R1C + 1]; }
-                                pt[c][0] = make_float2(a00, b00); pt[c][1] = make_float2(a01, b01);
-                                pb[c][0] = make_float2(a10, b1[c * WS_R1C]); pb[c][1] = make_float2(a11, b1[c * WS_R1C + 1]);
-                            }
-#else
 #pragma unroll
                             for (int c = 0; c < 5; c++) {
                                 q[c] = make_float2(R0s[(pr * 5 + c) * WS_SW], R0s[((pr + 1) * 5 + c) * WS_SW]);
                                 pt[c][0] = make_float2(a0[c * WS_R1C], b0[c * WS_R1C]); pt[c][1] = make_float2(a0[c * WS_R1C + 1], b0[c * WS_R1C + 1]);
                                 pb[c][0] = make_float2(a1[c * WS_R1C], b1[c * WS_R1C]); pb[c][1] = make_float2(a1[c * WS_R1C + 1], b1[c * WS_R1C + 1]);
                             }
-#endif
                             upd_core2(q, pt, pb, make_float2(fxr[pr], fxr[pr + 1]), make_float2(fyr[pr], fyr[pr + 1]), make_float2(dxs[pr], dxs[pr + 1]),
                                       make_float2(dys[pr], dys[pr + 1]), t.one, m);
                             const float ma[5] = {m[0].x, m[1].x, m[2].x, m[3].x, m[4].x}, mb[5] = {m[0].y, m[1].y, m[2].y, m[3].y, m[4].y};
