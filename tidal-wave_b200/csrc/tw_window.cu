@@ -126,7 +126,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     if (mbar_try(bar, parity)) return;
 #pragma unroll 1
-    for (unsigned it = 0; !mbar_try(bar, parity); ++it) {
+    for (unsigned it = 0; !mbar_try(bar, parity); ++it)
+        if (it > (1u << 26)) __trap();
+}
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int x, int y, int z, unsigned bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
