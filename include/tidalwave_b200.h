@@ -27,7 +27,7 @@ enum tw_error_code {
     TW_BAD_IMAGE_FORMAT = 2,
     TW_DONT_MATCH_SIZE = 3,
     TW_CUDA_ERROR = 4,   /* reason carries cudaGetErrorString */
-    TW_UNSUPPORTED = 5   /* reserved for documented gaps (currently unused) */
+    TW_UNSUPPORTED = 5   /* a documented gap (removed experimental options) */
 };
 
 /* Response.status, src/consumer.cpp:77,86 */
@@ -158,14 +158,14 @@ const char *tw_last_error(tw_ctx *ctx);
  *                     is not produced (tw_batch_flow fails after such a run; tw_flow is always dense).  Default 0 for
  *                     tw_create, 1 for the dispatcher's contexts (tw_pool_*; TW_SPARSE_LAST=0 turns it off there).
  *   "graph"      = 1 (default): repeated runs of one (size, batch, options) replay a captured CUDA graph.
- *   "gauss_fma"  = 1: symmetric fmaf in the Gaussian window tap sums on top of the faithful arithmetic (oracle relax bit 0).
- *   "update_fma" = 1: fmaf chains in the update matrices on top of "arithmetic" = 1 (oracle relax bit 6; studied, rejected
- *                     as a default: 0.157 px on the reference's scenario1 fixture).
+ *   "gauss_fma", "update_fma", "gauss_scalar": removed in round 2 (studied and rejected relaxations -- oracle relax bits 0 / 6 --
+ *                     and the scalar v1 window kernel); setting one to 1 answers TW_UNSUPPORTED.
  *   "window_tiles" = 0 / 1 / 2: the Gaussian window iterations of radius 15 run the persistent warp-specialised strip kernel
  *                     (tw_window.cu: TMA tensor-map rings, register-resident column walkers) / the tile-per-CTA kernel / (2, the
  *                     default) the strip kernel under the relaxed arithmetic and the tile kernel under the faithful one.  Same
  *                     arithmetic either way, bit-identical results; TW_WINDOW=strip|tiles|auto in the environment sets the default.
- *   "gauss_scalar", "level_generic", "level_unfused", "tight_pitch": alternative code paths kept for the parity tests. */
+ *   "level_generic", "level_unfused", "tight_pitch", "box_unfused": alternative code paths (also the fall-backs of unusual
+ *                     options) that the parity tests force. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);
 /* Process-wide default of "arithmetic" for contexts created afterwards (the dispatcher's consumers included). */
 int tw_set_default_arithmetic(int relaxed);

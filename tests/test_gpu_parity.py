@@ -125,18 +125,24 @@ def test_generic_kernel_paths(of, tw, oracle, kw):
 
 
 def test_kernel_variants_agree(tw, oracle):
-    """The scalar (v1) window kernel, the generic level-image kernel and the tight-pitch layout are alternative code paths
-    for the same arithmetic: all bit-identical to the default path."""
+    """The generic / unfused level-image kernels, the tight-pitch layout and both window kernels are alternative code paths for
+    the same arithmetic: all bit-identical to the oracle.  The experimental options removed in round 2 answer TW_UNSUPPORTED."""
     a, b = tw.synth.make_pair("S", 480, 300, 33, defect=True)
     ref = oracle.farneback(a, b, FlowParam())
-    for opt in (None, "gauss_scalar", "level_generic", "level_unfused", "tight_pitch"):
+    for opt in (None, "level_generic", "level_unfused", "tight_pitch", "window_tiles=0", "window_tiles=1"):
         o = tw.OpticalFlow(0, 480, 300, 1)
+        o.set_option("arithmetic", 0)
         if opt:
-            o.set_option(opt, 1)
+            name, _, val = opt.partition("=")
+            o.set_option(name, int(val or 1))
         rc, fx, fy, _ = o.calculateInternal(a, b)
         assert rc == 0
         assert np.array_equal(fx, ref[..., 0]) and np.array_equal(fy, ref[..., 1]), opt
         o.close()
+    o = tw.OpticalFlow(0, 480, 300, 1)
+    for gone in ("gauss_fma", "update_fma", "gauss_scalar"):
+        assert tw.load().tw_set_option(o.ctx, gone.encode(), 1) == 5 and tw.load().tw_set_option(o.ctx, gone.encode(), 0) == 0
+    o.close()
 
 
 def test_batch_equals_single(of, tw):

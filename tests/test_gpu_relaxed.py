@@ -108,26 +108,6 @@ def test_arithmetic_option_switches(tw, oracle):
     o.close()
 
 
-def test_update_fma_opt_in_is_relax_bit_6(tw, oracle):
-    """The studied (rejected as default) update-matrices relaxation stays reachable and is exactly oracle bit 6 on top of
-    the default relaxation; a defect pair with a motion boundary drives both the shared-row and the per-pixel epilogue paths."""
-    a, b = tw.synth.make_pair("S", 480, 300, 33, defect=True)
-    oracle.set_relax(RELAX_BITS | 64)
-    rel = oracle.farneback(a, b, FlowParam())
-    oracle.set_relax(0)
-    o = tw.OpticalFlow(0, 480, 300, 1)
-    o.set_option("update_fma", 1)
-    rc, fx, fy, _ = o.calculateInternal(a, b)
-    assert rc == 0 and np.array_equal(fx, rel[..., 0]) and np.array_equal(fy, rel[..., 1])
-    o.set_option("update_fma", 0)
-    oracle.set_relax(RELAX_BITS)
-    rel = oracle.farneback(a, b, FlowParam())
-    oracle.set_relax(0)
-    rc, fx, fy, _ = o.calculateInternal(a, b)
-    assert rc == 0 and np.array_equal(fx, rel[..., 0]) and np.array_equal(fy, rel[..., 1])
-    o.close()
-
-
 def test_relaxed_full_size_1080p(tw, oracle):
     """BASELINE configs[1] at full size (screenshot-like pair with a defect): relaxed default vs both oracles."""
     a, b = tw.synth.make_pair("S", 1920, 1080, 100, True)

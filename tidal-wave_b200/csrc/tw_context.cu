@@ -1245,12 +1245,14 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!ctx || !name) return TW_BAD_PARAMETER;
     if (!strcmp(name, "arithmetic")) { ctx->opt_arith = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "graph")) { ctx->opt_graph = value ? 1 : 0; if (!value) drop_graph(ctx); return TW_OK; }
-    if (!strcmp(name, "gauss_fma")) { ctx->opt_gauss_fma = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "gauss_fma") || !strcmp(name, "update_fma") || !strcmp(name, "gauss_scalar")) {
+        // studied and rejected relaxations (oracle relax bits 0 / 6) and the scalar v1 window kernel: no longer in the library
+        if (value) { ctx->err = std::string(name) + ": removed from the library (DESIGN.md section 2)"; return TW_UNSUPPORTED; }
+        return TW_OK;
+    }
     if (!strcmp(name, "sparse_last")) { ctx->opt_sparse_last = value ? 1 : 0; return TW_OK; }
-    if (!strcmp(name, "update_fma")) { ctx->opt_update_fma = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "box_unfused")) { ctx->opt_box_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value < 0 || value > 2 ? 2 : value; return TW_OK; }
-    if (!strcmp(name, "gauss_scalar")) { ctx->opt_gauss_scalar = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }

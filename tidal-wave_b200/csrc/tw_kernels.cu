@@ -1049,11 +1049,8 @@ __global__ void __launch_bounds__(256, 6) first_update_kernel(FirstUpdateArgs a)
 cudaError_t launch_first_update(cudaStream_t s, const FirstUpdateArgs &a)
 {
     dim3 grid((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.batch);
-    if (a.ufma) {
-        if (a.d.pitch == 2048) first_update_kernel<2048, true><<<grid, dim3(32, 8), 0, s>>>(a);
-        else if (a.d.pitch == 4096) first_update_kernel<4096, true><<<grid, dim3(32, 8), 0, s>>>(a);
-        else first_update_kernel<0, true><<<grid, dim3(32, 8), 0, s>>>(a);
-    } else {
+    if (a.ufma) return cudaErrorNotSupported; // "update_fma" was removed from the library (see launch_gauss_mr)
+    {
         if (a.d.pitch == 2048) first_update_kernel<2048, false><<<grid, dim3(32, 8), 0, s>>>(a);
         else if (a.d.pitch == 4096) first_update_kernel<4096, false><<<grid, dim3(32, 8), 0, s>>>(a);
         else first_update_kernel<0, false><<<grid, dim3(32, 8), 0, s>>>(a);
@@ -1127,8 +1124,7 @@ __global__ void __launch_bounds__(256) gauss_iter_generic_kernel(IterArgs a, Win
             f[o] = fx; f[o + plane] = fy;
         } else {
             float mm[5];
-            if (a.ufma) update_matrices_px<true>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
-            else update_matrices_px<false>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
+            update_matrices_px<false>(R0, R1, pitch, w, h, x, y, fx, fy, mm);
             store_M(a.Mout + (size_t)b * 5 * plane, pitch, y, x, mm);
         }
     }
@@ -1773,21 +1769,6 @@ static cudaError_t launch_gauss_fast2(cudaStream_t s, const IterArgs &a, const W
     return launch_gauss_fast2p<MR, FMA, UF, 0>(s, a, t);
 }
 
-template <int MR, int FMA, bool UF>
-static cudaError_t launch_gauss_fast(cudaStream_t s, const IterArgs &a, const WinTaps &t)
-{
-    static bool configured_dev[kMaxDevices] = {};
-    bool &configured = configured_dev[current_device()];
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gauss_iter_kernel<MR, FMA, UF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GK_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    dim3 grid((a.d.w + GK_TW - 1) / GK_TW, (a.d.h + GK_TH - 1) / GK_TH, a.batch);
-    gauss_iter_kernel<MR, FMA, UF><<<grid, 256, GK_SMEM, s>>>(a, t);
-    return cudaGetLastError();
-}
-
 // (window mode, ufma) combinations that exist: faithful (0,0), the gauss_fma opt-in (1,0), relaxed = direct form (2,0),
 // relaxed + the update_fma opt-in (2,1).
 template <int MR>
@@ -1797,16 +1778,12 @@ static cudaError_t launch_gauss_mr(cudaStream_t s, const IterArgs &a, const WinT
     if (MR == 15 && a.d.pitch == 2048 && a.fma == 2 && !a.ufma) return launch_gauss_fast2p<15, 2, false, 2048>(s, a, t);
     return cudaErrorNotSupported;
 #else
-    if (!a.scalar) {
-        if (a.fma == 2 && a.ufma) return launch_gauss_fast2<MR, 2, true>(s, a, t);
-        if (a.fma == 2) return launch_gauss_fast2<MR, 2, false>(s, a, t);
-        if (a.fma) return launch_gauss_fast2<MR, 1, false>(s, a, t);
-        return launch_gauss_fast2<MR, 0, false>(s, a, t);
-    }
-    if (a.fma == 2 && a.ufma) return launch_gauss_fast<MR, 2, true>(s, a, t);
-    if (a.fma == 2) return launch_gauss_fast<MR, 2, false>(s, a, t);
-    if (a.fma) return launch_gauss_fast<MR, 1, false>(s, a, t);
-    return launch_gauss_fast<MR, 0, false>(s, a, t);
+    // Only the two shipped arithmetics are instantiated.  The scalar (v1) kernel and the studied, rejected relaxations ("gauss_fma" =
+    // oracle relax bit 0, "update_fma" = bit 6) were removed from the library in round 2: the kernel templates
+    // still take FMA = 1 / UF = true, the oracle still restates the bits, but no binary code is carried for them.
+    if (a.scalar || a.ufma || a.fma == 1) return cudaErrorNotSupported;
+    if (a.fma == 2) return launch_gauss_fast2<MR, 2, false>(s, a, t);
+    return launch_gauss_fast2<MR, 0, false>(s, a, t);
 #endif
 }
 
