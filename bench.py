@@ -244,6 +244,51 @@ def run_pool(tw, lib, devices, B, cp, pinned, n_req, warm):
     return dt, nv
 
 
+def run_files_leg(tw, lib, device, B, cp, pairs, n_req=384):
+    """n_req pairs cycled from 16 distinct JPEG pairs on disk through tw_pool_submit_files; -> dict or None (no cv2 to write them)."""
+    import shutil
+    import tempfile
+    try:
+        import cv2
+    except Exception:
+        return None
+    d = tempfile.mkdtemp(prefix="tw_bench_files_")
+    try:
+        paths = []
+        for i, (a, b) in enumerate(pairs[:16]):
+            pa, pb = os.path.join(d, f"e{i}.jpg"), os.path.join(d, f"t{i}.jpg")
+            cv2.imwrite(pa, a, [cv2.IMWRITE_JPEG_QUALITY, 90]); cv2.imwrite(pb, b, [cv2.IMWRITE_JPEG_QUALITY, 90])
+            paths.append((pa.encode(), pb.encode()))
+        perr = C.create_string_buffer(256)
+        dv = (C.c_int * 1)(device)
+        pool = lib.tw_pool_create(dv, 1, W, H, B, C.byref(cp), 5.0, 10, 4096, perr, 256)
+        if not pool:
+            return None
+        threads = min(32, os.cpu_count() or 1)
+        lib.tw_pool_set_decoders(pool, threads)
+        rvec = (tw.tw_vector * 4096)()
+        rres = tw.tw_result()
+
+        def go(n):
+            ids = [lib.tw_pool_submit_files(pool, *paths[i % len(paths)]) for i in range(n)]
+            for i in ids:
+                if lib.tw_pool_wait(pool, i, rvec, 4096, C.byref(rres)) != 0:
+                    raise RuntimeError("file leg: " + rres.reason.decode())
+        try:
+            go(2 * B)
+            t0 = time.perf_counter()
+            go(n_req)
+            dt = time.perf_counter() - t0
+        finally:
+            lib.tw_pool_destroy(pool)
+        return {"value": n_req / dt, "unit": UNIT, "pairs": n_req, "seconds": dt, "decoder_threads": threads,
+                "api": "tw_pool_submit_files: %d pairs cycled from 16 distinct 1920x1080 JPEG pairs (cv2-written, quality 90) on disk; read + "
+                       "decoded by tw_decode_gray on %d host threads (bit-identical to cv2.imread), then one consumer on the GPU; bound by "
+                       "the host decode" % (n_req, threads)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,7 +392,7 @@ def main():
                 "families_note": "level_image is charged what the fused kernel moves: the u8 source ONCE for all four levels + the level "
                                  "images written (SURVEY's formula charges the source once per level)"}
 
-    e2e = variants = configs = e2e_inprocess = None
+    e2e = variants = configs = e2e_inprocess = e2e_files = None
     if not args.no_e2e:
         # ---- the other forms of the same step, beside the headline ----
         nv = max(20, args.steps // 4)
@@ -402,6 +447,12 @@ def main():
         for pa, pb in pinned:
             lib.tw_host_free(pa); lib.tw_host_free(pb)
 
+        # ---- file -> result: the reference's Manager::request takes two image PATHS (src/manager.cpp:68-78) and its consumers imread
+        # them (src/opticalflow.cpp:37,44).  Same here: tw_pool_submit_files, decode on the pool's C++ threads (host code, bit-identical
+        # to cv2.imread), then the same dispatcher.  This leg is bound by the host decode, not by the GPU. ----
+        if world == 1:
+            e2e_files = run_files_leg(tw, lib, local_rank, B, cp, pairs)
+
         # ---- BASELINE configs[2] and configs[3], device-resident, each against its own roofline (rank-local; N = 1 only) ----
         if world == 1:
             configs = {}
@@ -450,7 +501,7 @@ def main():
                            "parallelism": "independent pairs per GPU, no collective",
                            "l2": "256 MB memset between steps (inside the timed region) + per-step intermediates >> 126 MB L2",
                            "timed_region_s": elapsed_ms * 1e-3},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_inprocess": e2e_inprocess, "variants": variants, "configs": configs,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_inprocess": e2e_inprocess, "e2e_files": e2e_files, "variants": variants, "configs": configs,
                 "gpu_launches": int(launches), "clocks": clocks, "statuses": statuses}
         print(json.dumps(line), flush=True)
     dist.close()

@@ -209,8 +209,18 @@ tw_pool *tw_pool_create(const int *devices, int n_devices, int max_w, int max_h,
 /* Manager::request (src/manager.cpp:68-78): returns the request id (>= 0) or <0 if the pool is stopped. */
 long long tw_pool_submit(tw_pool *pool, const uint8_t *expect, int ew, int eh, const uint8_t *target, int tw,
                          int th);
+/* Manager::request exactly as the reference has it (src/manager.cpp:68-78, Request = two paths, src/message_queue.h:13-18): the
+ * files are read and decoded -- cv::imread(IMREAD_GRAYSCALE), src/opticalflow.cpp:37,44 -> tw_decode_gray -- on the pool's decoder
+ * threads (started on first use: one per host core, at most 32; tw_pool_set_decoders before the first call changes that), then join
+ * the same request queue.  Empty path -> TW_BAD_PARAMETER, unreadable / undecodable file -> TW_BAD_IMAGE_FORMAT "Can't open <path>"
+ * (src/opticalflow.cpp:20-49), sizes more than 5 px apart -> TW_DONT_MATCH_SIZE.  The pool owns the decoded images. */
+long long tw_pool_submit_files(tw_pool *pool, const char *expect_path, const char *target_path);
+int tw_pool_set_decoders(tw_pool *pool, int n);
 /* Blocks until request `id` is answered; copies up to cap vectors.  Returns res->code, or <0 if dropped. */
 int tw_pool_wait(tw_pool *pool, long long id, tw_vector *out, int cap, tw_result *res);
+/* Blocks until request `id` is answered and copies its result WITHOUT taking it (res->n_vectors = the room tw_pool_wait needs).
+ * Returns res->code, or <0 if dropped / unknown. */
+int tw_pool_peek(tw_pool *pool, long long id, tw_result *res);
 /* Non-blocking: 1 if answered (result copied), 0 if pending, <0 if dropped/unknown. */
 int tw_pool_poll(tw_pool *pool, long long id, tw_vector *out, int cap, tw_result *res);
 /* Report, src/message_queue.h:44-48: {request, data, error}. */

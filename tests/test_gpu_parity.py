@@ -407,3 +407,31 @@ def test_pipelined_batches_match_synchronous(tw):
             assert wr["status"] == names[st] and len(wr["vector"]) == nv
             assert [(v["x"], v["y"], v["dx"], v["dy"]) for v in wr["vector"]] == vs
     o.close()
+
+
+@pytest.mark.gpu
+def test_pool_path_requests(tw, golden, tmp_path):
+    """tw_pool_submit_files = Manager::request as the reference has it (two paths, src/manager.cpp:68-78): files read and decoded on
+    the pool's C++ decoder threads; answers equal those of the image-based requests; the reference's error messages
+    (src/opticalflow.cpp:20-61) for empty paths, unreadable files and mismatched sizes."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    s1 = os.path.join(gold, "jpg", "fixture_s1_capture1.jpg")
+    s2e, s2r = os.path.join(gold, "png", "fixture_s2_expected.png"), os.path.join(gold, "png", "fixture_s2_revision2.png")
+    (tmp_path / "junk.jpg").write_bytes(b"\xff\xd8\xff\xe0junk")
+    pool = tw.Pool([0], batch=4)  # vector_cap = 0: every vector
+    tw.load().tw_pool_set_decoders(pool.pool, 3)
+    want = pool.wait(pool.request(tw.imread_gray(s2e), tw.imread_gray(s2r)))
+    ids = [pool.request_files(*p) for p in ((s2e, s2r), (s1, s1), ("", s1), (s1, ""), (s2e, str(tmp_path / "junk.jpg")),
+                                            (str(tmp_path / "missing.png"), s1), (s1, s2e), (s2e, s2r))]
+    out = [pool.wait(i) for i in ids]
+    rep = pool.report()
+    pool.stop(); pool.close()
+    assert want["status"] == "SUSPICIOUS" and len(want["vector"]) == 24
+    for k in (0, 7):
+        assert out[k]["status"] == "SUSPICIOUS" and out[k]["vector"] == want["vector"] and (out[k]["width"], out[k]["height"]) == (180, 117)
+    assert out[1]["status"] == "OK" and (out[1]["width"], out[1]["height"]) == (280, 279)
+    assert [o["status"] for o in out[2:7]] == ["ERROR"] * 5
+    assert [o["reason"] for o in out[2:7]] == ["ExpectImagePath is empty.", "TargetImagePath is empty.", "Can't open " + str(tmp_path / "junk.jpg"),
+                                              "Can't open " + str(tmp_path / "missing.png"), "Don't match image size"]
+    assert rep == {"request": 9, "data": 4, "error": 5}

@@ -112,6 +112,10 @@ def load() -> C.CDLL:
                                  C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.tw_pool_submit.restype = C.c_longlong
     L.tw_pool_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.tw_pool_submit_files.restype = C.c_longlong
+    L.tw_pool_submit_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.tw_pool_set_decoders.argtypes = [C.c_void_p, C.c_int]
+    L.tw_pool_peek.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(tw_result)]
     L.tw_pool_wait.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(tw_vector), C.c_int, C.POINTER(tw_result)]
     L.tw_pool_poll.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(tw_vector), C.c_int, C.POINTER(tw_result)]
     L.tw_pool_report.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -310,12 +314,22 @@ class Pool:
             self._keep[rid] = (a, b)
         return rid
 
+    def request_files(self, expect_path: str, target_path: str) -> int:
+        """Manager::request with two image paths (src/manager.cpp:68-78): read + decoded on the pool's C++ decoder threads."""
+        return self.lib.tw_pool_submit_files(self.pool, (expect_path or "").encode(), (target_path or "").encode())
+
     def wait(self, rid: int) -> dict | None:
         cap = self.cap
         if cap <= 0:  # all vectors: the request's own sampling grid (src/consumer.cpp:60-76)
             a = self._keep.get(rid, (None, None))[0]
-            eh, ew = a.shape if a is not None else (0, 0)
-            cap = max(1, ((ew + self.span - 1) // self.span) * ((eh + self.span - 1) // self.span))
+            if a is not None:
+                eh, ew = a.shape
+                cap = max(1, ((ew + self.span - 1) // self.span) * ((eh + self.span - 1) // self.span))
+            else:  # path-based request: ask how many vectors there are
+                info = tw_result()
+                if self.lib.tw_pool_peek(self.pool, rid, C.byref(info)) < 0:
+                    return None
+                cap = max(1, info.n_vectors)
         vec = (tw_vector * cap)()
         res = tw_result()
         rc = self.lib.tw_pool_wait(self.pool, rid, vec, cap, C.byref(res))

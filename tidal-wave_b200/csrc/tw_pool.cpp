@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -25,10 +26,16 @@
 
 namespace {
 
-struct Request { // Request, src/message_queue.h:13-18 (paths replaced by decoded images)
+struct Request { // Request, src/message_queue.h:13-18 (decoded images; `own` holds them for path-based requests)
     long long id;
     const uint8_t *expect, *target;
     int ew, eh, tw, th;
+    std::shared_ptr<std::vector<uint8_t>> own_e, own_t;
+};
+
+struct FileJob { // Request as the reference has it: two paths (src/message_queue.h:13-18)
+    long long id;
+    std::string expect, target;
 };
 
 struct Slot {
@@ -48,6 +55,11 @@ struct tw_pool {
     std::mutex mu;
     std::condition_variable cv_req, cv_res;
     std::deque<Request> queue;
+    std::deque<FileJob> files;            // path-based requests waiting for a decoder thread
+    std::vector<std::thread> decoders;
+    std::condition_variable cv_file;
+    int decoding = 0;                     // jobs a decoder thread is working on
+    int n_decoders = 0;                   // 0: one per host core (at most 32)
     std::unordered_map<long long, Slot> slots;
     bool running = true;
     long long next_id = 0;
@@ -74,6 +86,67 @@ void publish(tw_pool *p, long long id, const tw_result &res, const tw_vector *ve
     if (nvec > 0) s.vectors.assign(vec, vec + nvec);
     s.done = true;
     if (res.status == TW_STATUS_ERROR) p->error_count++; else p->data_count++; // Manager::notify, src/manager.cpp:109-114
+}
+
+// imread of both paths (src/opticalflow.cpp:20-49) on a decoder thread, then the request joins the compute queue.
+bool read_file(const std::string &path, std::vector<uint8_t> &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    out.clear();
+    uint8_t buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + n);
+    fclose(f);
+    return !out.empty();
+}
+
+bool imread_gray(const std::string &path, std::vector<uint8_t> &raw, std::shared_ptr<std::vector<uint8_t>> &img, int &w, int &h)
+{
+    if (!read_file(path, raw)) return false;
+    if (tw_decode_gray(raw.data(), raw.size(), nullptr, 0, &w, &h) != TW_OK || w < 1 || h < 1) return false;
+    img = std::make_shared<std::vector<uint8_t>>((size_t)w * h);
+    return tw_decode_gray(raw.data(), raw.size(), img->data(), img->size(), &w, &h) == TW_OK;
+}
+
+void decoder_main(tw_pool *p)
+{
+    std::vector<uint8_t> raw;
+    for (;;) {
+        FileJob job;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_file.wait(lk, [&] { return !p->files.empty() || !p->running; });
+            if (!p->running) return;
+            job = std::move(p->files.front());
+            p->files.pop_front();
+            p->decoding++;
+        }
+        Request r{};
+        r.id = job.id;
+        tw_result e;
+        bool ok = true;
+        // src/opticalflow.cpp:20-49: empty paths are BadParameter, unreadable / undecodable files BadImageFormat "Can't open <path>"
+        if (job.expect.empty()) { fill_error(&e, TW_BAD_PARAMETER, "ExpectImagePath is empty."); ok = false; }
+        else if (job.target.empty()) { fill_error(&e, TW_BAD_PARAMETER, "TargetImagePath is empty."); ok = false; }
+        else if (!imread_gray(job.expect, raw, r.own_e, r.ew, r.eh)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.expect).c_str()); ok = false; }
+        else if (!imread_gray(job.target, raw, r.own_t, r.tw, r.th)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.target).c_str()); ok = false; }
+        if (!ok) {
+            publish(p, job.id, e, nullptr, 0);
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->decoding--;
+            p->cv_res.notify_all();
+            continue;
+        }
+        r.expect = r.own_e->data(); r.target = r.own_t->data();
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->decoding--;
+            if (!p->running) { p->slots[r.id].dropped = true; p->cv_res.notify_all(); return; }
+            p->queue.push_back(std::move(r));
+        }
+        p->cv_req.notify_one();
+    }
 }
 
 // Consumer::run, src/consumer.cpp:42-94
@@ -249,6 +322,37 @@ long long tw_pool_submit(tw_pool *p, const uint8_t *expect, int ew, int eh, cons
     return id;
 }
 
+// Manager::request as the reference has it (src/manager.cpp:68-78): two image PATHS.  The files are read and decoded on the pool's
+// decoder threads (cv::imread(IMREAD_GRAYSCALE), src/opticalflow.cpp:37,44 -> tw_decode_gray), started on first use.
+long long tw_pool_submit_files(tw_pool *p, const char *expect_path, const char *target_path)
+{
+    if (!p) return -1;
+    long long id;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (!p->running) return -1;
+        if (p->decoders.empty()) {
+            int n = p->n_decoders > 0 ? p->n_decoders : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+            for (int i = 0; i < n; i++) p->decoders.emplace_back(decoder_main, p);
+        }
+        id = p->next_id++;
+        p->slots[id];
+        p->files.push_back(FileJob{id, expect_path ? expect_path : "", target_path ? target_path : ""});
+        p->request_count++;
+    }
+    p->cv_file.notify_one();
+    return id;
+}
+
+int tw_pool_set_decoders(tw_pool *p, int n)
+{
+    if (!p || n < 1) return TW_BAD_PARAMETER;
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->decoders.empty()) return TW_BAD_PARAMETER; // already started
+    p->n_decoders = n;
+    return TW_OK;
+}
+
 int tw_pool_wait(tw_pool *p, long long id, tw_vector *out, int cap, tw_result *res)
 {
     if (!p) return -1;
@@ -258,6 +362,20 @@ int tw_pool_wait(tw_pool *p, long long id, tw_vector *out, int cap, tw_result *r
     p->cv_res.wait(lk, [&] { it = p->slots.find(id); return it == p->slots.end() || it->second.done || it->second.dropped; });
     if (it == p->slots.end()) return -1;
     return take(p, it, out, cap, res);
+}
+
+// Blocks until request `id` is answered and copies its tw_result WITHOUT taking it: res->n_vectors tells the caller how many
+// vectors tw_pool_wait will need room for (path-based requests: the caller does not know the image size beforehand).
+int tw_pool_peek(tw_pool *p, long long id, tw_result *res)
+{
+    if (!p || !res) return -1;
+    std::unique_lock<std::mutex> lk(p->mu);
+    auto it = p->slots.find(id);
+    if (it == p->slots.end()) return -1;
+    p->cv_res.wait(lk, [&] { it = p->slots.find(id); return it == p->slots.end() || it->second.done || it->second.dropped; });
+    if (it == p->slots.end() || it->second.dropped) return -1;
+    *res = it->second.res;
+    return res->code;
 }
 
 int tw_pool_poll(tw_pool *p, long long id, tw_vector *out, int cap, tw_result *res)
@@ -286,14 +404,24 @@ void tw_pool_stop(tw_pool *p)
     if (!p) return;
     {
         std::lock_guard<std::mutex> lk(p->mu);
-        if (!p->running && p->consumers.empty()) return;
+        if (!p->running && p->consumers.empty() && p->decoders.empty()) return;
         p->running = false;
         // pending requests are dropped (tryPop returns false once stopped, src/message_queue.h:75-78)
         for (auto &r : p->queue) p->slots[r.id].dropped = true;
         p->queue.clear();
+        for (auto &f : p->files) p->slots[f.id].dropped = true;
+        p->files.clear();
     }
     p->cv_req.notify_all();
+    p->cv_file.notify_all();
     p->cv_res.notify_all();
+    for (auto &t : p->decoders) if (t.joinable()) t.join();
+    p->decoders.clear();
+    {   // a decoder that was mid-job when the pool stopped may have queued its request: drop it like the others
+        std::lock_guard<std::mutex> lk(p->mu);
+        for (auto &r : p->queue) p->slots[r.id].dropped = true;
+        p->queue.clear();
+    }
     for (auto &t : p->consumers) if (t.joinable()) t.join();
     p->consumers.clear();
     p->cv_res.notify_all();

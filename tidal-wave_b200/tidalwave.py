@@ -42,7 +42,6 @@ class TidalWave:
         self._batch = batch
         self._pool = None
         self._disposed = False
-        self._decoders = None  # numThreads decode workers: the reference decodes inside its consumer threads (src/consumer.cpp:54)
 
     # EventEmitter
     def on(self, event, fn):
@@ -61,6 +60,7 @@ class TidalWave:
             devices = self._devices or [i % ndev for i in range(max(1, self.numThreads))]  # consumer i <-> GPU i % count
             # screenshot directories mix page sizes: no size bound, and every vector of every pair comes back whatever its size
             self._pool = Pool(devices, self.param, self.threshold, self.span, max_w=0, max_h=0, batch=self._batch, vector_cap=0)
+            load().tw_pool_set_decoders(self._pool.pool, max(1, self.numThreads))
         return self._pool
 
     def calc(self, expected: str, target: str):
@@ -73,37 +73,15 @@ class TidalWave:
             self._pending.append((None, expected, target, "ExpectImagePath is empty.")); return
         if not target:
             self._pending.append((None, expected, target, "TargetImagePath is empty.")); return
-        if self._decoders is None:
-            from concurrent.futures import ThreadPoolExecutor
-            from .api import load
-            load()  # bind the library on this thread before the workers use it
-            self._decoders = ThreadPoolExecutor(max_workers=max(1, self.numThreads))
-        # the two imreads run on a decode worker (tw_decode_gray releases the GIL); the pair is queued once both are in
-        self._pending.append((self._decoders.submit(self._decode_pair, expected, target), expected, target, None))
-
-    @staticmethod
-    def _decode_pair(expected, target):
-        """The imread half of OpticalFlow::calculate (src/opticalflow.cpp:37-49): (expect, target, None) or (None, None, message)."""
-        a = imread_gray(expected)
-        if a is None:
-            return None, None, "Can't open " + expected
-        b = imread_gray(target)
-        if b is None:
-            return None, None, "Can't open " + target
-        return a, b, None
+        # Manager::request with the two paths: the imreads run on the dispatcher's C++ decoder threads (numThreads of them, as the
+        # reference decodes inside its numThreads consumers, src/consumer.cpp:54), the pair joins the compute queue when both are in
+        pool = self._ensure_pool(0, 0)
+        self._pending.append((pool.request_files(expected, target), expected, target, None))
 
     def flush(self):
         """Delivers every outstanding answer as 'data' / 'error' events (the uv_async hop of src/manager.cpp:102-125)."""
         pending, self._pending = self._pending, []
-        queued = []
-        for fut, expected, target, err in pending:  # request order: decoded pairs go to the dispatcher as they become ready
-            rid = None
-            if err is None:
-                a, b, err = fut.result()
-                if err is None:
-                    pool = self._ensure_pool(max(a.shape[1], b.shape[1]), max(a.shape[0], b.shape[0]))
-                    rid = pool.request(a, b)
-            queued.append((rid, expected, target, err))
+        queued = pending  # (request id | None, expected, target, error message | None), in request order
         for rid, expected, target, err in queued:
             if err is None:
                 r = self._pool.wait(rid)
@@ -127,9 +105,6 @@ class TidalWave:
             return
         self.flush()
         self._disposed = True
-        if self._decoders is not None:
-            self._decoders.shutdown(wait=True)
-            self._decoders = None
         if self._pool is not None:
             self._pool.stop()
             self._pool.close()
