@@ -339,10 +339,12 @@ def test_context_size_bound_is_enforced(tw):
     o.close()
 
 
-@pytest.mark.parametrize("size,seed,batch", [((1920, 1080), 100, 2), ((500, 333), 7, 3), ((97, 61), 9, 1), ((960, 540), 11, 1)])
+@pytest.mark.parametrize("size,seed,batch", [((1920, 1080), 100, 2), ((500, 333), 7, 3), ((97, 61), 9, 1), ((960, 540), 11, 1),
+                                             ((40, 33), 3, 2), ((70, 130), 5, 1), ((64, 64), 6, 1), ((129, 72), 8, 2)])
 def test_strip_window_kernel_bit_identical(tw, oracle, size, seed, batch):
     """The persistent strip window kernel ("window_tiles" = 0) and the tile kernel run the same arithmetic: bit-identical to
-    each other and to the oracle in both arithmetics, on ragged strip / group geometry (w % 96 != 0, h % 8 != 0), with a defect
+    each other and to the oracle in both arithmetics, on ragged strip / group geometry (w % 64 != 0, h % 8 != 0, frames narrower than
+    one strip and shorter than one segment), with a defect
     (motion boundary: the global-memory gather path of the epilogue), on the last and the non-last iterations, batched."""
     w, h = size
     a, b = tw.synth.make_pair("S", w, h, seed, defect=True)

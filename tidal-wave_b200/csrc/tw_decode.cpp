@@ -34,7 +34,10 @@ int decode_pgm(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int
         while (pos < n && (b[pos] == ' ' || b[pos] == '\n' || b[pos] == '\r' || b[pos] == '\t')) pos++;
         if (pos < n && b[pos] == '#') { while (pos < n && b[pos] != '\n') pos++; continue; }
         int v = 0, digits = 0;
-        while (pos < n && b[pos] >= '0' && b[pos] <= '9') { v = v * 10 + (b[pos] - '0'); pos++; digits++; }
+        while (pos < n && b[pos] >= '0' && b[pos] <= '9') {
+            if (++digits > 7) return TW_BAD_IMAGE_FORMAT; // bounded: no signed overflow on a long digit string
+            v = v * 10 + (b[pos] - '0'); pos++;
+        }
         if (!digits) return TW_BAD_IMAGE_FORMAT;
         vals[got++] = v;
     }

@@ -9,6 +9,8 @@
 #include "tw_kernels.cuh"
 #include "tw_device.cuh"
 
+#include <atomic>
+
 namespace tw {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was configured per device, not
@@ -186,8 +188,8 @@ size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int
 cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a)
 {
     size_t smem = level_image_smem_bytes(a.smem_w, a.smem_h, a.tile_w, a.ksize, a.identity);
-    static size_t configured_dev[kMaxDevices][2] = {};
-    size_t *configured = configured_dev[current_device()];
+    static std::atomic<size_t> configured_dev[kMaxDevices][2];
+    std::atomic<size_t> *configured = configured_dev[current_device()];
     if (smem > 48 * 1024 && smem > configured[a.identity ? 1 : 0]) {
         cudaError_t e = a.identity ? cudaFuncSetAttribute(level_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                    : cudaFuncSetAttribute(level_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -373,8 +375,8 @@ template <int S, int K, int TWO, int THO>
 static cudaError_t launch_pyr(cudaStream_t s, const LevelFastArgs &fa, int nimg)
 {
     using G = PyrGeom<S, K, TWO, THO>;
-    static bool configured_dev[kMaxDevices] = {};
-    bool &configured = configured_dev[current_device()];
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool> &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(level_pyr_kernel<S, K, TWO, THO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         if (e != cudaSuccess) return e;
@@ -568,8 +570,8 @@ __global__ void __launch_bounds__(256) level_fused_kernel(LevelFusedArgs a)
 cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H, int spitch, float *const dst[4], const LevelDims d[4],
                                const float *k8, const float *k4, const float *k2, const float *k1, int nimg)
 {
-    static bool configured_dev[kMaxDevices] = {};
-    bool &configured = configured_dev[current_device()];
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool> &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(level_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM);
         if (e != cudaSuccess) return e;
@@ -1749,8 +1751,8 @@ __global__ void __launch_bounds__(256, 2) gauss_iter2_kernel(IterArgs a, WinTaps
 template <int MR, int FMA, bool UF, int PITCH>
 static cudaError_t launch_gauss_fast2p(cudaStream_t s, const IterArgs &a, const WinTaps &t)
 {
-    static bool configured_dev[kMaxDevices] = {};
-    bool &configured = configured_dev[current_device()];
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool> &configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gauss_iter2_kernel<MR, FMA, UF, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
         if (e != cudaSuccess) return e;
@@ -2188,7 +2190,7 @@ cudaError_t launch_box_ckpt(cudaStream_t s, const float *Min, double *CK, const 
 cudaError_t launch_box_band(cudaStream_t s, const float *Min, const double *CK, const float *R, float *Mout, float *flow, const LevelDims &d,
                             int batch, int m, int winSize, int last)
 {
-    static bool configured_dev[kMaxDevices][2] = {};
+    static std::atomic<bool> configured_dev[kMaxDevices][2];
     BoxBandArgs a{};
     a.Min = Min; a.CK = CK; a.R = R; a.Mout = Mout; a.flow = flow; a.d = d; a.m = m; a.nb = (d.h + BX_BH - 1) / BX_BH;
     a.scale = 1. / ((double)winSize * winSize);

@@ -45,6 +45,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -741,7 +742,7 @@ int sm_count()
 template <int FMA, bool LAST>
 cudaError_t launch_strip(cudaStream_t s, const StripMaps &m, const StripArgs &sa, const WinTaps &t, int grid)
 {
-    static bool configured_dev[64] = {};
+    static std::atomic<bool> configured_dev[64]; // consumer threads sharing a device may get here together; the attribute call is idempotent
     int d = 0;
     cudaGetDevice(&d);
     if (d < 0 || d >= 64) d = 0;
