@@ -276,6 +276,7 @@ void poly_tables(int n, double sigma, PolyTables &t)
     t.n = n;
     t.ig11 = inv[1][1]; t.ig03 = inv[0][3]; t.ig33 = inv[3][3]; t.ig55 = inv[5][5];
     t.fig11 = (float)t.ig11; t.fig55 = (float)t.ig55;
+    t.one = 1.0f;
     for (int x = 0; x <= n; x++) {
         t.g[x] = g[x]; t.xg[x] = xg[x]; t.xxg[x] = xxg[x];
         t.gd[x] = (double)g[x]; t.xxgd[x] = (double)xxg[x];

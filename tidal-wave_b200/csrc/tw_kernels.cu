@@ -777,9 +777,9 @@ __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restri
 // unchanged.  The same arithmetic is restated in oracle/farneback_ref.c under twref_set_relax(16): the GPU result is
 // checked bit for bit against that, and against the faithful oracle within the north-star tolerance
 // (measured <= 2.6e-4 px at 1920x1080, 2.1e-3 px on the reference's fixture; tools/relax_study.py).
-//   tile 96 x 32, 256 threads; phase V: thread = (column, 16-row group), 16 + 2N inputs in registers;
+//   tile 96 x 32, 256 threads; phase V: thread = (column pair, 8-row group), 8 + 2N float2 inputs in registers, packed f32x2;
 //   phase H: thread = 4 adjacent pixels, LDS.128 (lane stride 16 B: conflict-free), float4 stores.
-constexpr int PM_TW = 96, PM_TH = 32, PM_VW = 112, PM_RV = 16;
+constexpr int PM_TW = 96, PM_TH = 32, PM_VW = 112, PM_RV = 8;
 
 template <int N, int PITCH>
 __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__restrict__ I, float *__restrict__ R, LevelDims d, PolyTables t)
@@ -791,36 +791,47 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
     const int w = d.w, h = d.h, pitch = PITCH ? PITCH : d.pitch;
     const bool interior = (y0 - N >= 0) && (y0 + PM_TH + N - 1 <= h - 1); // block-uniform
 
-    if (tid < 2 * PM_VW) {
-        const int g = tid / PM_VW, j = tid - g * PM_VW;
-        const int gx = clampi(x0 - 8 + j, 0, w - 1);
+    // phase V, packed f32x2: thread = (column PAIR, 8-row group); every operation of App. A.3's vertical pass is issued once for the
+    // two columns (each half one IEEE operation, so the values are those of the scalar form; the rounded sum "acc + k * p" is
+    // fma(k * p, one, acc) with the runtime 1.0f, see tw_fma2)
+    if (tid < (PM_VW / 2) * (PM_TH / PM_RV)) {
+        const int g = tid / (PM_VW / 2), jj = tid - g * (PM_VW / 2);
+        const int xa = x0 - 8 + 2 * jj;
         const int ybase = y0 + g * PM_RV - N;
-        float in[PM_RV + 2 * N];
-        if (interior) {
+        const bool pairok = xa >= 0 && xa + 1 <= w - 1; // both columns inside: one 8-byte load per row
+        const int ga = clampi(xa, 0, w - 1), gb = clampi(xa + 1, 0, w - 1);
+        float2 in[PM_RV + 2 * N];
+        if (interior && pairok) {
             const unsigned rsb = (unsigned)pitch * 4u;
-            const char *p = row_ptr(reinterpret_cast<const char *>(img + gx), rsb, (unsigned)ybase);
+            const char *p = row_ptr(reinterpret_cast<const char *>(img + xa), rsb, (unsigned)ybase);
 #pragma unroll
             for (int r = 0; r < PM_RV + 2 * N; r++) {
-                if (PITCH) in[r] = __ldg(reinterpret_cast<const float *>(p) + (size_t)r * PITCH);
-                else in[r] = __ldg(reinterpret_cast<const float *>(row_ptr(p, rsb, (unsigned)r)));
+                if (PITCH) in[r] = __ldg(reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(p) + (size_t)r * PITCH));
+                else in[r] = __ldg(reinterpret_cast<const float2 *>(row_ptr(p, rsb, (unsigned)r)));
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < PM_RV + 2 * N; r++) in[r] = __ldg(img + (size_t)clampi(ybase + r, 0, h - 1) * pitch + gx);
+            for (int r = 0; r < PM_RV + 2 * N; r++) {
+                const float *row = img + (size_t)clampi(ybase + r, 0, h - 1) * pitch;
+                in[r] = make_float2(__ldg(row + ga), __ldg(row + gb));
+            }
         }
+        const float2 one2 = make_float2(t.one, t.one);
 #pragma unroll
         for (int o = 0; o < PM_RV; o++) {
-            float r0 = in[o + N] * t.g[0], r1 = 0.f, r2 = 0.f;
+            float2 r0 = tw_mul2(in[o + N], make_float2(t.g[0], t.g[0])), r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 1; k <= N; k++) {
-                float up = in[o + N - k], dn = in[o + N + k];
-                float p = up + dn, q = dn - up;
-                r0 = r0 + t.g[k] * p;
-                r1 = r1 + t.xg[k] * q;
-                r2 = r2 + t.xxg[k] * p;
+                const float2 up = in[o + N - k], dn = in[o + N + k];
+                const float2 p = tw_add2(up, dn), q = tw_sub2(dn, up);
+                r0 = tw_fma2(tw_mul2(make_float2(t.g[k], t.g[k]), p), one2, r0);
+                r1 = tw_fma2(tw_mul2(make_float2(t.xg[k], t.xg[k]), q), one2, r1);
+                r2 = tw_fma2(tw_mul2(make_float2(t.xxg[k], t.xxg[k]), p), one2, r2);
             }
-            const int si = (g * PM_RV + o) * PM_VW + j;
-            sm[0][si] = r0; sm[1][si] = r1; sm[2][si] = r2;
+            const int si = (g * PM_RV + o) * PM_VW + 2 * jj;
+            *reinterpret_cast<float2 *>(&sm[0][si]) = r0;
+            *reinterpret_cast<float2 *>(&sm[1][si]) = r1;
+            *reinterpret_cast<float2 *>(&sm[2][si]) = r2;
         }
     }
     __syncthreads();
@@ -845,7 +856,7 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
                 v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
             }
         };
-        // plane 0 (r0): b1, b4 in double, b2 in float
+        // plane 0 (r0): b1, b4 in double; b2 in float, two pixels per packed fmaf (each half the scalar fmaf of oracle relax bit 4)
         load_plane(0);
 #pragma unroll
         for (int q = 0; q < NV; q++) dv[q] = (double)v[q];
@@ -853,17 +864,24 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
         for (int px = 0; px < 4; px++) {
             const int ctr = px + 8 - LO;
             double b1 = dv[ctr] * t.gd[0], b4 = 0.0;
-            float b2 = 0.f;
 #pragma unroll
             for (int k = 1; k <= N; k++) {
                 const double tg = dv[ctr + k] + dv[ctr - k];
                 b1 = fma(tg, t.gd[k], b1);
                 b4 = fma(tg, t.xxgd[k], b4);
-                b2 = fmaf(v[ctr + k] - v[ctr - k], t.xg[k], b2);
             }
             t1[px] = b1 * t.ig03;
-            res[1][px] = b2 * t.fig11;
             res[3][px] = (float)(t1[px] + b4 * t.ig33);
+        }
+#pragma unroll
+        for (int px = 0; px < 4; px += 2) {
+            const int ctr = px + 8 - LO;
+            float2 b2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k <= N; k++)
+                b2 = tw_fma2(make_float2(v[ctr + k] - v[ctr - k], v[ctr + 1 + k] - v[ctr + 1 - k]), make_float2(t.xg[k], t.xg[k]), b2);
+            res[1][px] = b2.x * t.fig11;
+            res[1][px + 1] = b2.y * t.fig11;
         }
         // plane 2 (r2): b5 in double
         load_plane(2);
@@ -877,19 +895,17 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
             for (int k = 1; k <= N; k++) b5 = fma(dv[ctr + k] + dv[ctr - k], t.gd[k], b5);
             res[2][px] = (float)(t1[px] + b5 * t.ig33);
         }
-        // plane 1 (r1): b3, b6 in float
+        // plane 1 (r1): b3, b6 in float, packed as (b3, b6): fmaf(sum, g, b3) and fmaf(diff, xg, b6) in one instruction
         load_plane(1);
 #pragma unroll
         for (int px = 0; px < 4; px++) {
             const int ctr = px + 8 - LO;
-            float b3 = v[ctr] * t.g[0], b6 = 0.f;
+            float2 b36 = make_float2(v[ctr] * t.g[0], 0.f);
 #pragma unroll
-            for (int k = 1; k <= N; k++) {
-                b3 = fmaf(v[ctr + k] + v[ctr - k], t.g[k], b3);
-                b6 = fmaf(v[ctr + k] - v[ctr - k], t.xg[k], b6);
-            }
-            res[0][px] = b3 * t.fig11;
-            res[4][px] = b6 * t.fig55;
+            for (int k = 1; k <= N; k++)
+                b36 = tw_fma2(make_float2(v[ctr + k] + v[ctr - k], v[ctr + k] - v[ctr - k]), make_float2(t.g[k], t.xg[k]), b36);
+            res[0][px] = b36.x * t.fig11;
+            res[4][px] = b36.y * t.fig55;
         }
         const size_t o = (size_t)gy * 5 * pitch + gx; // row-interleaved R
         if (gx + 3 < w) {

@@ -19,6 +19,7 @@ struct PolyTables {
     double gd[kMaxPolyN + 1], xxgd[kMaxPolyN + 1]; // (double)g[k], (double)xxg[k]: no conversions in the tap loop
     double ig11, ig03, ig33, ig55;
     float fig11, fig55; // (float)ig11, (float)ig55: relaxed-arithmetic kernel
+    float one;          // 1.0f, deliberately a runtime value (packed f32x2 accumulate: see tw_fma2 in tw_device.cuh)
     int n;
 };
 
