@@ -50,6 +50,7 @@ struct Plan {
     uint8_t *src = nullptr; // [B][2][H][spitch]
     int spitch = 0;
     double *V = nullptr; // box only
+    float *T = nullptr;  // long pre-blur levels only: row-pass intermediate of launch_level_image_big
     bool fused_levels = false;
 };
 
@@ -448,6 +449,12 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
                           pl.scales[nsc - 2].ksize == 3 && pl.scales[nsc - 3].int_scale == 4 && pl.scales[nsc - 3].ksize == 9 &&
                           pl.scales[nsc - 4].int_scale == 8 && pl.scales[nsc - 4].ksize == 19 && (9 + 2 < std::min(W, H));
     }
+    {   // row-pass intermediate for levels behind a long pre-blur that no exact-integer fast path takes (deep pyramids)
+        size_t nT = 0;
+        for (const Scale &s : pl.scales)
+            if (!s.identity && s.ksize >= 31 && !(s.int_scale == 16 && s.ksize == 39)) nT = std::max(nT, level_image_big_floats(H, s.d.w, 2 * B));
+        if (nT && !dev_alloc(ctx, &pl.T, nT)) return false;
+    }
     if (p.flags == 0) { // box window: V planes of the three-launch form, or the band checkpoints of the fused form ([B][ceil(h/32)][5 * pitch])
         size_t nV = (size_t)B * 5 * (size_t)(fine.d.w + 32) * (size_t)(fine.d.h + 32);
         for (const Scale &s : pl.scales) nV = std::max(nV, (size_t)B * (size_t)((s.d.h + 31) / 32) * 5 * (size_t)s.d.pitch);
@@ -574,6 +581,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
         if (!fused_levels || si < fbase) {
             LaunchScope ls_(ctx, F_LEVEL, n * (2 * P0 + 8 * Pl));
             cudaError_t e_ = ctx->opt_level_generic ? cudaErrorNotSupported : launch_level_image_fast(ctx->stream, la, s.host_taps.data(), s.int_scale);
+            if (e_ == cudaErrorNotSupported && !ctx->opt_level_generic && pl.T && level_image_big_ok(la)) e_ = launch_level_image_big(ctx->stream, la, pl.T);
             if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
             if (e_ != cudaSuccess) { set_err(ctx, "launch_level_image", e_); return false; }
         }

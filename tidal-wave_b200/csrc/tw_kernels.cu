@@ -180,6 +180,102 @@ __global__ void __launch_bounds__(256) level_image_kernel(LevelImageArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1, long pre-blur kernels (deep pyramids: the 1/32-scale level of config 3 blurs with 79 taps before a non-integer
+// down-scale).  A tile of the generic kernel would stage (32 * tile + 79)^2 source pixels to produce a handful of outputs; here
+// the separable blur runs as two small kernels through an intermediate in global memory (L2-resident):
+//   level_rows_kernel: one CTA per (source row, image): the row is staged once as floats (REFLECT_101 halo), the row pass is
+//                      evaluated at the 2 source columns each output column reads -> T[image][row][2w]
+//   level_cols_kernel: one thread per output pixel: column pass at the 2 rows x 2 columns it reads (rows through REFLECT_101),
+//                      then the bilinear blend.
+// Same operations in the same order as level_image_kernel (App. A.2a / A.2b): bit-identical.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) level_rows_kernel(LevelImageArgs a, float *__restrict__ T, int tpitch)
+{
+    extern __shared__ float lr_smem[]; // [W + 2c] padded by one word per 32 (the slots of a warp are 32 source columns apart) | K taps
+    const int K = a.ksize, c = K / 2, W = a.W;
+    const int n = W + 2 * c;
+    float *row = lr_smem, *ktab = lr_smem + n + (n >> 5) + 1;
+    const int y = blockIdx.x;
+    const uint8_t *srow = a.src + ((size_t)blockIdx.y * a.H + y) * a.spitch;
+    for (int i = threadIdx.x; i < K; i += 256) ktab[i] = a.taps[i];
+    // interior columns as 4-byte words (all loads of a thread in flight together), the two REFLECT_101 halos and a ragged tail as bytes
+    const int W4 = W & ~3;
+#pragma unroll 4
+    for (int q4 = threadIdx.x; q4 < W4 / 4; q4 += 256) {
+        const unsigned wd = __ldg(reinterpret_cast<const unsigned *>(srow) + q4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = c + 4 * q4 + i;
+            row[q + (q >> 5)] = __uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * c + (W - W4); i += 256) {
+        const int q = i < c ? i : i < 2 * c ? W + i : W4 + c + (i - 2 * c); // left halo | right halo | tail columns
+        row[q + (q >> 5)] = u8_to_float(__ldg(srow + reflect1(q - c, W)));
+    }
+    __syncthreads();
+    float *out = T + ((size_t)blockIdx.y * a.H + y) * tpitch;
+    for (int slot = threadIdx.x; slot < 2 * a.d.w; slot += 256) {
+        const int xs = min(a.xi[slot >> 1] + (slot & 1), W - 1); // tap j reads source column xs - c + j = staged entry xs + j
+        float o = row[xs + (xs >> 5)] * ktab[0];
+#pragma unroll 4
+        for (int j = 1; j < K; j++) {
+            const int q = xs + j;
+            o = fmaf(row[q + (q >> 5)], ktab[j], o);
+        }
+        out[slot] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) level_cols_kernel(LevelImageArgs a, const float *__restrict__ T, int tpitch)
+{
+    const int d = blockIdx.x * 32 + (threadIdx.x & 31), e = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (d >= a.d.w || e >= a.d.h) return;
+    const int K = a.ksize, c = K / 2, H = a.H;
+    const float *Tb = T + (size_t)blockIdx.z * H * tpitch + 2 * d;
+    const int y0 = a.yi[e], y1 = min(y0 + 1, H - 1);
+    float res[2][2];
+#pragma unroll
+    for (int yy = 0; yy < 2; yy++) {
+        const int yc = yy ? y1 : y0;
+        float o0 = 0.f, o1 = 0.f;
+        {
+            const float2 q = __ldg(reinterpret_cast<const float2 *>(Tb + (size_t)yc * tpitch));
+            o0 = q.x * __ldg(a.taps + c); o1 = q.y * __ldg(a.taps + c);
+        }
+        for (int j = 1; j <= c; j++) {
+            const float2 up = __ldg(reinterpret_cast<const float2 *>(Tb + (size_t)reflect1(yc - j, H) * tpitch));
+            const float2 dn = __ldg(reinterpret_cast<const float2 *>(Tb + (size_t)reflect1(yc + j, H) * tpitch));
+            const float kk = __ldg(a.taps + c + j);
+            o0 = fmaf(up.x + dn.x, kk, o0);
+            o1 = fmaf(up.y + dn.y, kk, o1);
+        }
+        res[yy][0] = o0; res[yy][1] = o1;
+    }
+    const float fx = a.xf[d], gx = 1.f - fx, fy = a.yf[e], gy = 1.f - fy;
+    const float r0 = res[0][0] * gx + res[0][1] * fx;
+    const float r1 = res[1][0] * gx + res[1][1] * fx;
+    a.dst[(size_t)blockIdx.z * a.d.plane + (size_t)e * a.d.pitch + d] = r0 * gy + r1 * fy;
+}
+
+bool level_image_big_ok(const LevelImageArgs &a) { return !a.identity && !a.small && a.ksize >= 31 && a.ksize / 2 < a.W && a.ksize / 2 < a.H; }
+size_t level_image_big_floats(int H, int w, int nimg) { return (size_t)nimg * H * ((2 * w + 31) & ~31); }
+
+cudaError_t launch_level_image_big(cudaStream_t s, const LevelImageArgs &a, float *T)
+{
+    if (!level_image_big_ok(a) || !T) return cudaErrorNotSupported;
+    const int tpitch = (2 * a.d.w + 31) & ~31;
+    const int n = a.W + 2 * (a.ksize / 2);
+    const size_t smem = sizeof(float) * (size_t)(n + (n >> 5) + 1 + a.ksize);
+    if (smem > 48 * 1024) return cudaErrorNotSupported;
+    level_rows_kernel<<<dim3(a.H, a.nimg), 256, smem, s>>>(a, T, tpitch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    level_cols_kernel<<<dim3((a.d.w + 31) / 32, (a.d.h + 7) / 8, a.nimg), 256, 0, s>>>(a, T, tpitch);
+    return cudaGetLastError();
+}
+
 size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int identity)
 {
     return sizeof(float) * ((size_t)smem_h * smem_w + (size_t)smem_h * (identity ? tile_w : tile_w * 2) + ksize);

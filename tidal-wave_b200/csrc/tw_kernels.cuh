@@ -53,6 +53,11 @@ cudaError_t launch_level_image(cudaStream_t s, const LevelImageArgs &a);
 // Fast paths (full-resolution level; exact integer down-scales 2/4/8/16).  int_scale = S if W == w*S, H == h*S and the
 // resize tables are exactly (S*d + S/2 - 1, 0.5), else 0.  Returns cudaErrorNotSupported if none applies.
 cudaError_t launch_level_image_fast(cudaStream_t s, const LevelImageArgs &a, const float *host_taps, int int_scale);
+// Long pre-blur kernels (ksize >= 31, not an exact integer down-scale): separable blur through an intermediate T in global memory
+// ([nimg][H][roundup(2w, 32)] floats, level_image_big_floats): two small launches instead of huge shared-memory tiles.
+bool level_image_big_ok(const LevelImageArgs &a);
+size_t level_image_big_floats(int H, int w, int nimg);
+cudaError_t launch_level_image_big(cudaStream_t s, const LevelImageArgs &a, float *T);
 // All four level images of the default pyramid (S = 8, 4, 2, 1 with 19/9/3/3-tap pre-blurs) from one staged source tile.
 cudaError_t launch_level_fused(cudaStream_t s, const uint8_t *src, int W, int H, int spitch, float *const dst[4], const LevelDims d[4],
                                const float *k8, const float *k4, const float *k2, const float *k1, int nimg);
