@@ -160,10 +160,10 @@ const char *tw_last_error(tw_ctx *ctx);
  *   "graph"      = 1 (default): repeated runs of one (size, batch, options) replay a captured CUDA graph.
  *   "gauss_fma", "update_fma", "gauss_scalar": removed in round 2 (studied and rejected relaxations -- oracle relax bits 0 / 6 --
  *                     and the scalar v1 window kernel); setting one to 1 answers TW_UNSUPPORTED.
- *   "window_tiles" = 0 / 1 / 2: the Gaussian window iterations of radius 15 run the persistent warp-specialised strip kernel
- *                     (tw_window.cu: TMA tensor-map rings, register-resident column walkers) / the tile-per-CTA kernel / (2, the
- *                     default) the strip kernel under the relaxed arithmetic and the tile kernel under the faithful one.  Same
- *                     arithmetic either way, bit-identical results; TW_WINDOW=strip|tiles|auto in the environment sets the default.
+ *   "window_tiles" = 1 (default) / 0: the Gaussian window iterations of radius 15 run the tile-per-CTA kernel / the persistent
+ *                     warp-specialised strip kernel (tw_window.cu: TMA tensor-map rings, register-resident column walkers,
+ *                     setmaxnreg).  Same arithmetic, bit-identical results; the strip kernel measures 1-7 % slower (DESIGN.md
+ *                     section 4.2), so it is opt-in; TW_WINDOW=strip|tiles in the environment sets the default.
  *   "level_generic", "level_unfused", "tight_pitch", "box_unfused": alternative code paths (also the fall-backs of unusual
  *                     options) that the parity tests force. */
 int tw_set_option(tw_ctx *ctx, const char *name, int value);

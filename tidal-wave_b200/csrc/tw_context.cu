@@ -68,8 +68,8 @@ struct tw_ctx {
     int opt_update_fma = 0; // studied opt-in (oracle relax bit 6), never part of "arithmetic" = 1
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
     int opt_box_unfused = 0;  // 1: the three-launch box iteration (V plane through HBM), kept for the parity tests
-    int opt_window_tiles = 2; // 0: the persistent strip kernel (tw_window.cu); 1: the tile-per-CTA kernel (gauss_iter2_kernel); 2 (default): the strip
-                              // kernel for the relaxed arithmetic, the tile kernel for the faithful one (each where it is the faster)
+    int opt_window_tiles = 1; // 1 (default): the tile-per-CTA window kernel (gauss_iter2_kernel); 0: the persistent TMA-fed strip kernel (tw_window.cu),
+                              // bit-identical and measured 1-7 % slower
     int opt_arith = 1;  // 0 = faithful (App. A operation order), 1 = relaxed where validated (relaxed_in_effect)
     int opt_graph = 1;  // replay the launch sequence of a batch from a captured CUDA graph
     // CUDA graph of the launch sequence (enqueue) for one (plan, n, threshold, span, options) key
@@ -613,7 +613,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             if (ia.span > 0 && sparse_in_effect(ctx, span)) {
                 // classification only: blur + solve at the sampled positions (one pass over M, no flow plane written)
                 LAUNCH(F_GLAST, n * 20.0 * Pl, launch_gauss_last_sparse(ctx->stream, ia, pl.win));
-            } else if ((p.flags & 256) && (ctx->opt_window_tiles == 0 || (ctx->opt_window_tiles == 2 && ia.fma == 2)) && gauss_strip_ok(ia, pl.win) &&
+            } else if ((p.flags & 256) && ctx->opt_window_tiles == 0 && gauss_strip_ok(ia, pl.win) &&
                        s.maps[Min == s.M1 ? 1 : 0].valid) {
                 LAUNCH(ia.last ? F_GLAST : F_GITER, bytes, launch_gauss_strip(ctx->stream, ia, pl.win, s.maps[Min == s.M1 ? 1 : 0]));
             } else if (p.flags & 256) {
@@ -657,7 +657,7 @@ bool run_sequence(tw_ctx *ctx, int n, double threshold, int span)
     if (!ctx->opt_graph || ctx->profiling) return enqueue(ctx, n, threshold, span);
     tw_ctx::GraphKey key;
     key.plan_gen = ctx->plan_gen; key.n = n; key.thr = threshold; key.span = span;
-    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5 | ctx->opt_sparse_last << 6 | ctx->opt_window_tiles << 7 /* 2 bits */ | ctx->opt_box_unfused << 9;
+    key.opts = ctx->opt_gauss_fma | ctx->opt_gauss_scalar << 1 | ctx->opt_level_generic << 2 | ctx->opt_level_unfused << 3 | ctx->opt_arith << 4 | ctx->opt_update_fma << 5 | ctx->opt_sparse_last << 6 | ctx->opt_window_tiles << 7 | ctx->opt_box_unfused << 9;
     key.vectors = ctx->d_vectors; key.dev_cap = ctx->dev_cap; // the captured sample kernel bakes both in
     if (ctx->graph_exec && key == ctx->graph_key) {
         cudaError_t e = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
@@ -769,7 +769,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
     ctx->opt_arith = default_arith();
     if (const char *g = getenv("TW_GRAPH")) ctx->opt_graph = atoi(g) ? 1 : 0; // TW_GRAPH=0: eager launches (profilers)
-    if (const char *g = getenv("TW_WINDOW")) ctx->opt_window_tiles = !strcmp(g, "strip") ? 0 : !strcmp(g, "tiles") ? 1 : 2; // TW_WINDOW=strip|tiles|auto
+    if (const char *g = getenv("TW_WINDOW")) ctx->opt_window_tiles = !strcmp(g, "strip") ? 0 : 1; // TW_WINDOW=strip|tiles
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
     cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
     if ((e = cudaMalloc(&ctx->d_counts, sizeof(int) * ctx->max_batch)) != cudaSuccess ||
@@ -1261,7 +1261,7 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     }
     if (!strcmp(name, "sparse_last")) { ctx->opt_sparse_last = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "box_unfused")) { ctx->opt_box_unfused = value ? 1 : 0; return TW_OK; }
-    if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value < 0 || value > 2 ? 2 : value; return TW_OK; }
+    if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }

@@ -35,8 +35,9 @@
 // the producers' polling sat on the V warps' critical path); 64-column strips with a dedicated producer warp at 96 registers and
 // eight software-pipelined H / U warps (2 pixels per lane: too little ILP) 23 % slower; the same with the producer replaced by
 // "the last consumer of a slot refills it" 40 % slower (the refill code and its atomics moved onto the consumers' critical
-// path).  This form equals the tile kernel in the relaxed arithmetic (2.36 vs 2.33 ms per step), is 12 % faster at 3840x2160 and
-// 5 % slower in the faithful arithmetic (three packed instructions per tap pair instead of two).
+// path).  This form comes within 1-2 % of the tile kernel at 1920x1080 in the relaxed arithmetic (2.36 vs 2.33 ms per step) and is
+// 5-7 % slower in the faithful arithmetic (three packed instructions per tap pair instead of two) and at 3840x2160: it is an
+// opt-in ("window_tiles" = 0, TW_WINDOW=strip), the tile kernel stays the default.
 //
 // Arithmetic per output is exactly that of gauss_iter2_kernel (tw_kernels.cu): FMA = 0 the oracle's add-mul-add order
 // (bit-identical to oracle/farneback_ref.c), FMA = 2 the direct-form fmaf taps of the relaxed default (oracle relax bit 7).
