@@ -437,3 +437,46 @@ def test_pool_path_requests(tw, golden, tmp_path):
     assert [o["reason"] for o in out[2:7]] == ["ExpectImagePath is empty.", "TargetImagePath is empty.", "Can't open " + str(tmp_path / "junk.jpg"),
                                               "Can't open " + str(tmp_path / "missing.png"), "Don't match image size"]
     assert rep == {"request": 9, "data": 4, "error": 5}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,kw", [((203, 157), dict(flags=0, winSize=2)), ((203, 157), dict(flags=0, winSize=9, polyN=5, polySigma=1.1)),
+                                     ((330, 97), dict(flags=0, winSize=31)), ((97, 330), dict(flags=0, winSize=32)),
+                                     ((203, 157), dict(flags=0, winSize=34)), ((64, 33), dict(flags=0, winSize=15))])
+def test_box_window_fused_and_unfused_bit_identical(tw, oracle, size, kw):
+    """The fused box iteration (band checkpoints + band kernel, window radius <= 16) and the three-launch form ("box_unfused", also the
+    fall-back for larger radii: winSize 34 -> radius 17) follow App. A.6's running sums in the oracle's order: bit-identical to the
+    oracle and to each other on ragged frames (w, h not multiples of 32), frames smaller than a band / a chunk, even and odd sizes."""
+    w, h = size
+    pairs = [tw.synth.make_pair("S", w, h, 3, defect=True), tw.synth.make_pair("T", w, h, 4)]
+    ref = [oracle.farneback(a, b, FlowParam(**kw)) for a, b in pairs]
+    o = tw.OpticalFlow(0, w, h, 2)
+    p = tw.OpticalFlowParameter(**kw)
+    for unfused in (0, 1):
+        o.set_option("box_unfused", unfused)
+        for _ in range(2):  # eager, then the captured graph
+            res = o.calculate_batch(pairs, p, threshold=0.5)
+            for i in range(2):
+                fx, fy = o.batch_flow(i, w, h)
+                assert np.array_equal(fx, ref[i][..., 0]) and np.array_equal(fy, ref[i][..., 1]), (unfused, i)
+        status, vec = oracle.sample(ref[0], 10, 0.5)
+        assert res[0]["status"] == status and _vec_pos(res[0]) == [(v[0], v[1]) for v in vec]
+    o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,levels", [((500, 333), 5), ((700, 200), 4), ((130, 900), 5)])
+def test_deep_pyramid_long_preblur_levels(tw, oracle, size, levels):
+    """Deep pyramids put 39- / 79-tap pre-blurs in front of non-integer down-scales: the separable two-kernel level path
+    (level_rows / level_cols) and the generic kernel ("level_generic") are bit-identical to the oracle."""
+    w, h = size
+    a, b = tw.synth.make_pair("S", w, h, 21, defect=True)
+    kw = dict(pyrLevels=levels, pyrIterations=2)
+    ref = oracle.farneback(a, b, FlowParam(**kw))
+    for generic in (0, 1):
+        o = tw.OpticalFlow(0, w, h, 1)
+        o.set_option("arithmetic", 0)
+        o.set_option("level_generic", generic)
+        rc, fx, fy, _ = o.calculateInternal(a, b, tw.OpticalFlowParameter(**kw))
+        assert rc == 0 and np.array_equal(fx, ref[..., 0]) and np.array_equal(fy, ref[..., 1]), generic
+        o.close()
