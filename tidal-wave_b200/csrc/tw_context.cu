@@ -457,7 +457,7 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
     }
     if (p.flags == 0) { // box window: V planes of the three-launch form, or the band checkpoints of the fused form ([B][ceil(h/32)][5 * pitch])
         size_t nV = (size_t)B * 5 * (size_t)(fine.d.w + 32) * (size_t)(fine.d.h + 32);
-        for (const Scale &s : pl.scales) nV = std::max(nV, (size_t)B * (size_t)((s.d.h + 31) / 32) * 5 * (size_t)s.d.pitch);
+        for (const Scale &s : pl.scales) nV = std::max(nV, (size_t)B * (size_t)((s.d.h + box_band_height() - 1) / box_band_height()) * 5 * (size_t)s.d.pitch);
         if (!dev_alloc(ctx, &pl.V, nV)) return false;
     }
     pl.valid = true;

@@ -2143,7 +2143,7 @@ cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, cons
 //                      bilinear gather) -> M', or on the last iteration the flow store.
 //              Every running sum is evaluated in the oracle's order (App. A.6); nothing is re-associated.
 // ------------------------------------------------------------------------------------------------
-constexpr int BX_BH = 32, BX_CW = 32, BX_THREADS = 256, BX_MAXM = 16;
+constexpr int BX_BH = 32, BX_CW = 32, BX_THREADS = 256, BX_MAXM = 16; // (16-row bands at 4 CTAs / SM measured slower: 1 293 vs 1 485 pairs/s)
 __host__ __device__ constexpr int bx_vpitch(int nv) { return ((5 * nv + 10) / 16) * 16 + 5; } // doubles; = 5 mod 16, >= 5 * nv
 constexpr int BX_BPITCH = 165;                                                              // doubles per row of the b tile (= 5 mod 16)
 
@@ -2251,7 +2251,7 @@ __global__ void __launch_bounds__(BX_THREADS, 2) box_band_kernel(BoxBandArgs a)
         {
             const int lx = tid & 31, ly = tid >> 5, x = x0 + lx;
 #pragma unroll 1
-            for (int jp = 0; jp < 4; jp += 2) {
+            for (int jp = 0; jp < BX_BH / 8; jp += 2) {
                 float fx[2], fy[2];
                 bool ok[2];
 #pragma unroll
@@ -2289,6 +2289,7 @@ __global__ void __launch_bounds__(BX_THREADS, 2) box_band_kernel(BoxBandArgs a)
     }
 }
 
+int box_band_height() { return BX_BH; }
 bool box_fused_ok(const LevelDims &d, int m) { return m >= 1 && m <= BX_MAXM && d.w >= 1 && d.h >= 1; }
 
 cudaError_t launch_box_ckpt(cudaStream_t s, const float *Min, double *CK, const LevelDims &d, int batch, int m)

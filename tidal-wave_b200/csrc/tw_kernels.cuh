@@ -122,10 +122,11 @@ cudaError_t launch_gauss_last_sparse(cudaStream_t s, const IterArgs &a, const Wi
 // is launch_first_update with flow_in.
 cudaError_t launch_box_vsum(cudaStream_t s, const float *Min, double *VT, const LevelDims &d, int batch, int m);
 cudaError_t launch_box_hscan(cudaStream_t s, const double *VT, float *flow, const LevelDims &d, int batch, int m, int winSize);
-// Fused form (m <= 16): launch_box_ckpt keeps only the vertical running sums at the top of every 32-row band (CK: [B][ceil(h/32)]
+// Fused form (m <= 16): launch_box_ckpt keeps only the vertical running sums at the top of every band of box_band_height() rows (CK: [B][bands]
 // [5 * pitch] doubles); launch_box_band re-runs them inside each band from its checkpoint, continues the horizontal running sums
 // across the band and goes straight on to the solve and the next update-matrices (or the flow store): no V plane in HBM.
 bool box_fused_ok(const LevelDims &d, int m);
+int box_band_height(); // rows per band: CK holds ceil(h / box_band_height()) checkpoints per pair
 cudaError_t launch_box_ckpt(cudaStream_t s, const float *Min, double *CK, const LevelDims &d, int batch, int m);
 cudaError_t launch_box_band(cudaStream_t s, const float *Min, const double *CK, const float *R, float *Mout, float *flow, const LevelDims &d,
                             int batch, int m, int winSize, int last);
