@@ -2162,18 +2162,16 @@ __global__ void __launch_bounds__(128) box_ckpt_kernel(const float *__restrict__
     for (int y = 1; y < m; y++) vs = vs + (double)M[(size_t)min(y, h - 1) * rs];
     for (int y0 = 0; y0 < h; y0 += BX_BH) {
         ck[(size_t)(y0 / BX_BH) * rs] = vs;
+        // the scan is latency-bound: all 2 x 32 loads of a band are in flight before the first dependent addition
+        float diff[BX_BH];
 #pragma unroll
-        for (int q = 0; q < BX_BH; q += 16) {
-            float diff[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int y = y0 + q + k;
-                diff[k] = __ldg(M + (size_t)min(y + m, h - 1) * rs) - __ldg(M + (size_t)max(min(y, h - 1) - m - 1, 0) * rs);
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                if (y0 + q + k < h) vs = vs + (double)diff[k];
+        for (int k = 0; k < BX_BH; k++) {
+            const int y = y0 + k;
+            diff[k] = __ldg(M + (size_t)min(y + m, h - 1) * rs) - __ldg(M + (size_t)max(min(y, h - 1) - m - 1, 0) * rs);
         }
+#pragma unroll
+        for (int k = 0; k < BX_BH; k++)
+            if (y0 + k < h) vs = vs + (double)diff[k];
     }
 }
 
