@@ -14,7 +14,11 @@ $CMD > $o/${tag}_plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock
 $CMD > $o/${tag}_plain2.log 2>&1 && ncu --set full --clock-control none -k regex:"gauss_strip|gauss_iter2|gauss_last_sparse|polyexp|first_update|level_" -s 63 -c 21 -o /tmp/prof_${tag} $CMD > $o/${tag}_ncu_full.log 2>&1; echo "full rc=$?"
 python tools/ncu_summary.py /tmp/prof_${tag}.ncu-rep $o/${tag}_ncu_full_step_batch16.csv
 python tools/ncu_traffic.py $o/${tag}_ncu_full_step_batch16.csv 16 relaxed > $o/${tag}_traffic.json
-# source-level capture of a level-0 launch of the window kernel (the strip kernel launches 11 times per step; indices 9, 10 are the finest scale)
-$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_strip" -s 20 -c 1 -f -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
+# source-level capture of a level-0 launch of the window kernel (tile kernel: 11 launches per step incl. the dense lasts of the coarser scales; 9, 10 = finest)
+$CMD > $o/${tag}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gauss_iter2" -s 42 -c 1 -f -o $o/${tag}_window_level0 $CMD > $o/${tag}_ncu_window.log 2>&1; echo "window rc=$?"
+# the same launch of the opt-in strip kernel (TW_WINDOW=strip: 11 launches per step, indices 9 and 10 are the finest scale)
+TW_WINDOW=strip ncu --set full --clock-control none --import-source on -k regex:"gauss_strip" -s 20 -c 1 -f -o $o/${tag}_strip_level0 $CMD > $o/${tag}_ncu_strip.log 2>&1; echo "strip rc=$?"
+TW_WINDOW=strip python bench.py --no-cpu --no-e2e --steps 100 > $o/${tag}_bench_strip.json 2>> $o/${tag}_bench.err
+python __graft_entry__.py smoke > $o/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
 python tools/cfg_bench.py cfg3 > $o/${tag}_cfg3.json 2>> $o/${tag}_bench.err; python tools/cfg_bench.py cfg4 > $o/${tag}_cfg4.json 2>> $o/${tag}_bench.err
 ls -la $o | grep ${tag}
