@@ -128,6 +128,8 @@ int tw_pipe_submit(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8
                    const tw_flow_param *param, double threshold, int span);
 int tw_pipe_collect(tw_ctx *ctx, tw_vector *out, int cap, tw_result *res);
 int tw_pipe_pending(tw_ctx *ctx);
+/* 1 if the oldest pending batch has finished on the device (tw_pipe_collect would not block), else 0. */
+int tw_pipe_ready(tw_ctx *ctx);
 
 /* ---- split phases of tw_compare_batch (same stream; used by the dispatcher to overlap, and by the
  * benchmark to time the device-resident pass separately from the PCIe legs) ---- */

@@ -83,6 +83,7 @@ def load() -> C.CDLL:
     L.tw_pipe_submit.argtypes = [C.c_void_p, C.c_int, u8pp, u8pp, C.c_int, C.c_int, C.c_int, C.POINTER(tw_flow_param), C.c_double, C.c_int]
     L.tw_pipe_collect.argtypes = [C.c_void_p, C.POINTER(tw_vector), C.c_int, C.POINTER(tw_result)]
     L.tw_pipe_pending.argtypes = [C.c_void_p]
+    L.tw_pipe_ready.argtypes = [C.c_void_p]
     L.tw_batch_upload.argtypes = [C.c_void_p, C.c_int, u8pp, u8pp, C.c_int, C.c_int, C.c_int]
     L.tw_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(tw_flow_param), C.c_double, C.c_int]
     L.tw_batch_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(tw_vector), C.c_int, C.POINTER(tw_result)]

@@ -1032,6 +1032,14 @@ int tw_compare_batch(tw_ctx *ctx, int n, const uint8_t *const *expect, const uin
 // Consumer thread per GPU, /root/reference/src/consumer.cpp:18-24, 42-94).
 int tw_pipe_pending(tw_ctx *ctx) { return ctx ? ctx->pipe.count : 0; }
 
+// 1 if the oldest batch in flight has finished on the device (tw_pipe_collect would not block), 0 if it is still running or nothing
+// is in flight.
+int tw_pipe_ready(tw_ctx *ctx)
+{
+    if (!ctx || ctx->pipe.count < 1) return 0;
+    return cudaEventQuery(ctx->pipe.slot[ctx->pipe.head].done) == cudaSuccess ? 1 : 0;
+}
+
 int tw_pipe_submit(tw_ctx *ctx, int n, const uint8_t *const *expect, const uint8_t *const *target, int w, int h, int stride,
                    const tw_flow_param *param, double threshold, int span)
 {

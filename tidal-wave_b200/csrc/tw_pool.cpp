@@ -198,12 +198,12 @@ void consumer_main(tw_pool *p, int idx)
                 work.push_back(p->queue.front());
                 p->queue.pop_front();
                 // batch: take the following requests while they are compute-ready and have the same size; while the GPU is
-                // still busy with an earlier batch there is time to let a short queue fill up (bounded: <= 20 x 50 us)
+                // still busy with an earlier batch there is time to let a short queue fill up (until that batch is done, at most 20 x 50 us)
                 const Request h = work[0];
                 const bool head_ok = h.expect && h.target && h.ew == h.tw && h.eh == h.th;
                 for (int spins = 0; head_ok && (int)work.size() < p->batch; ) {
                     if (p->queue.empty()) {
-                        if (inflight.empty() || spins++ >= 20 || !p->running) break;
+                        if (inflight.empty() || spins++ >= 20 || !p->running || tw_pipe_ready(ctx)) break;
                         p->cv_req.wait_for(lk, std::chrono::microseconds(50));
                         continue;
                     }
