@@ -161,3 +161,20 @@ def test_graph_replay_equals_eager(tw, arith):
     got = g.calculate_batch(pairs)
     assert [x["vector"] for x in got] == [x["vector"] for x in want]
     g.close()
+
+
+@pytest.mark.gpu
+def test_polyexp_tma_tiles_bit_identical(tw, oracle):
+    """"polyexp_tma" = 1 stages the interior input tiles of the relaxed polynomial expansion with a TMA tensor-map copy; border tiles keep
+    the per-thread loads.  Same values in, same arithmetic: bit-identical to oracle(144) on a frame with interior and border tiles."""
+    a, b = tw.synth.make_pair("S", 700, 300, 41, defect=True)
+    oracle.set_relax(RELAX_BITS)
+    rel = oracle.farneback(a, b, FlowParam())
+    oracle.set_relax(0)
+    for tma in (1, 0):
+        o = tw.OpticalFlow(0, 700, 300, 1)
+        o.set_option("polyexp_tma", tma)
+        for _ in range(2):
+            rc, fx, fy, _ = o.calculateInternal(a, b)
+            assert rc == 0 and np.array_equal(fx, rel[..., 0]) and np.array_equal(fy, rel[..., 1]), tma
+        o.close()

@@ -37,6 +37,7 @@ struct Scale {
     // buffers (alias the shared work buffers unless keep_levels)
     float *I = nullptr, *R = nullptr, *M0 = nullptr, *M1 = nullptr, *flow = nullptr;
     StripMaps maps[2] = {}; // tensor maps of the strip window kernel reading M0 / M1 (and R) at this scale
+    TileMap imap = {};      // tensor map of the level images (poly-exp input tiles by TMA)
 };
 
 struct Plan {
@@ -67,6 +68,8 @@ struct tw_ctx {
     bool last_sparse = false; // the previous run left no dense field
     int opt_update_fma = 0; // studied opt-in (oracle relax bit 6), never part of "arithmetic" = 1
     int opt_gauss_fma = 0, opt_gauss_scalar = 0, opt_level_generic = 0, opt_level_unfused = 0, opt_tight_pitch = 0;
+    int opt_poly_no_tma = 1;  // 0 ("polyexp_tma" = 1, TW_POLY_TMA=1): interior input tiles of the relaxed poly-exp staged by one TMA tile copy --
+                              // bit-identical, measured 5 % slower than the per-thread loads (0.697 vs 0.662 ms per step), hence opt-in
     int opt_box_unfused = 0;  // 1: the three-launch box iteration (V plane through HBM), kept for the parity tests
     int opt_window_tiles = 1; // 1 (default): the tile-per-CTA window kernel (gauss_iter2_kernel); 0: the persistent TMA-fed strip kernel (tw_window.cu),
                               // bit-identical and measured 1-7 % slower
@@ -436,6 +439,8 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
             s.R = R; s.M0 = M0; s.M1 = M1;
         }
         s.maps[0].valid = s.maps[1].valid = 0;
+        s.imap.valid = 0;
+        if (!ctx->opt_poly_no_tma) make_polyexp_map(s.I, s.d, 2 * B, p.polyN, &s.imap);
         if ((p.flags & 256) && pl.win.m == 15) { // no tensor maps (old driver?): the tile kernel runs instead
             make_strip_maps(s.M0, s.R, s.d, B, &s.maps[0]);
             make_strip_maps(s.M1, s.R, s.d, B, &s.maps[1]);
@@ -585,7 +590,7 @@ bool enqueue(tw_ctx *ctx, int n, double threshold, int span)
             if (e_ == cudaErrorNotSupported) e_ = launch_level_image(ctx->stream, la);
             if (e_ != cudaSuccess) { set_err(ctx, "launch_level_image", e_); return false; }
         }
-        LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly, relaxed ? 1 : 0));
+        LAUNCH(F_POLY, n * 48 * Pl, launch_polyexp(ctx->stream, s.I, s.R, s.d, 2 * n, pl.poly, relaxed ? 1 : 0, &s.imap));
 
         FirstUpdateArgs fa{};
         if (si > 0) {
@@ -769,6 +774,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
     ctx->opt_arith = default_arith();
     if (const char *g = getenv("TW_GRAPH")) ctx->opt_graph = atoi(g) ? 1 : 0; // TW_GRAPH=0: eager launches (profilers)
+    if (const char *g = getenv("TW_POLY_TMA")) ctx->opt_poly_no_tma = atoi(g) ? 0 : 1;
     if (const char *g = getenv("TW_WINDOW")) ctx->opt_window_tiles = !strcmp(g, "strip") ? 0 : 1; // TW_WINDOW=strip|tiles
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
     cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1);
@@ -1268,6 +1274,11 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
         return TW_OK;
     }
     if (!strcmp(name, "sparse_last")) { ctx->opt_sparse_last = value ? 1 : 0; return TW_OK; }
+    if (!strcmp(name, "polyexp_tma")) { // takes effect when the next plan is built (the tensor maps are made with the plan)
+        ctx->opt_poly_no_tma = value ? 0 : 1;
+        ctx->plan.valid = false;
+        return TW_OK;
+    }
     if (!strcmp(name, "box_unfused")) { ctx->opt_box_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }

@@ -878,15 +878,40 @@ __global__ void __launch_bounds__(256) polyexp_fast_kernel(const float *__restri
 constexpr int PM_TW = 96, PM_TH = 32, PM_VW = 112, PM_RV = 8;
 
 template <int N, int PITCH>
-__global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__restrict__ I, float *__restrict__ R, LevelDims d, PolyTables t)
+__global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__restrict__ I, float *__restrict__ R, LevelDims d, PolyTables t,
+                                                               const __grid_constant__ TileMap imap)
 {
-    __shared__ __align__(16) float sm[3][PM_TH * PM_VW];
+    // dynamic shared memory: input tile staged by TMA [PM_TH + 2N][PM_VW] (interior tiles) | mbarrier | the three V planes
+    extern __shared__ __align__(128) unsigned char pm_smem[];
+    float *sin_ = reinterpret_cast<float *>(pm_smem);
+    constexpr int PM_IN_BYTES = (PM_TH + 2 * N) * PM_VW * 4;
+    constexpr int PM_BAR_OFF = (PM_IN_BYTES + 127) & ~127;
+    float (*sm)[PM_TH * PM_VW] = reinterpret_cast<float (*)[PM_TH * PM_VW]>(pm_smem + PM_BAR_OFF + 128);
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PM_TW, y0 = blockIdx.y * PM_TH;
     const float *img = I + (size_t)blockIdx.z * d.plane;
     const int w = d.w, h = d.h, pitch = PITCH ? PITCH : d.pitch;
     const bool interior = (y0 - N >= 0) && (y0 + PM_TH + N - 1 <= h - 1); // block-uniform
 
+    // Interior tiles (the whole 112 x (32 + 2N) input window inside the frame): ONE tensor-map TMA copy stages the tile
+    // (cp.async.bulk.tensor, UTMALDG); tiles that touch the frame border keep the per-thread loads with the replicate clamp.
+    const bool tma_tile = imap.valid && interior && x0 - 8 >= 0 && x0 - 8 + PM_VW <= w;
+    if (tma_tile) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(pm_smem + PM_BAR_OFF);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)PM_IN_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(pm_smem)),
+                         "l"(reinterpret_cast<unsigned long long>(&imap)), "r"(bar), "r"(x0 - 8), "r"(y0 - N), "r"((int)blockIdx.z)
+                         : "memory");
+        }
+        __syncthreads(); // the barrier is initialised before anybody probes it
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+    }
     // phase V, packed f32x2: thread = (column PAIR, 8-row group); every operation of App. A.3's vertical pass is issued once for the
     // two columns (each half one IEEE operation, so the values are those of the scalar form; the rounded sum "acc + k * p" is
     // fma(k * p, one, acc) with the runtime 1.0f, see tw_fma2)
@@ -897,7 +922,10 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
         const bool pairok = xa >= 0 && xa + 1 <= w - 1; // both columns inside: one 8-byte load per row
         const int ga = clampi(xa, 0, w - 1), gb = clampi(xa + 1, 0, w - 1);
         float2 in[PM_RV + 2 * N];
-        if (interior && pairok) {
+        if (tma_tile) {
+#pragma unroll
+            for (int r = 0; r < PM_RV + 2 * N; r++) in[r] = *reinterpret_cast<const float2 *>(sin_ + (g * PM_RV + r) * PM_VW + 2 * jj);
+        } else if (interior && pairok) {
             const unsigned rsb = (unsigned)pitch * 4u;
             const char *p = row_ptr(reinterpret_cast<const char *>(img + xa), rsb, (unsigned)ybase);
 #pragma unroll
@@ -1019,20 +1047,36 @@ __global__ void __launch_bounds__(256, 2) polyexp_mixed_kernel(const float *__re
     }
 }
 
-template <int N>
-static cudaError_t launch_polyexp_mixed(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t)
+template <int N, int PITCH>
+static cudaError_t launch_polyexp_mixed_p(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, const TileMap &imap)
 {
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool> &configured = configured_dev[current_device()];
+    constexpr int smem = (((PM_TH + 2 * N) * PM_VW * 4 + 127) & ~127) + 128 + 3 * PM_TH * PM_VW * 4;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(polyexp_mixed_kernel<N, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     dim3 grid((d.w + PM_TW - 1) / PM_TW, (d.h + PM_TH - 1) / PM_TH, nimg);
-    if (d.pitch == 2048) polyexp_mixed_kernel<N, 2048><<<grid, 256, 0, s>>>(I, R, d, t);
-    else if (d.pitch == 4096) polyexp_mixed_kernel<N, 4096><<<grid, 256, 0, s>>>(I, R, d, t);
-    else polyexp_mixed_kernel<N, 0><<<grid, 256, 0, s>>>(I, R, d, t);
+    polyexp_mixed_kernel<N, PITCH><<<grid, 256, smem, s>>>(I, R, d, t, imap);
     return cudaGetLastError();
 }
 
-cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, int relaxed)
+template <int N>
+static cudaError_t launch_polyexp_mixed(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, const TileMap *imap)
 {
-    if (relaxed && t.n == 7) return launch_polyexp_mixed<7>(s, I, R, d, nimg, t);
-    if (relaxed && t.n == 5) return launch_polyexp_mixed<5>(s, I, R, d, nimg, t);
+    TileMap none{};
+    const TileMap &m = (imap && imap->valid) ? *imap : none;
+    if (d.pitch == 2048) return launch_polyexp_mixed_p<N, 2048>(s, I, R, d, nimg, t, m);
+    if (d.pitch == 4096) return launch_polyexp_mixed_p<N, 4096>(s, I, R, d, nimg, t, m);
+    return launch_polyexp_mixed_p<N, 0>(s, I, R, d, nimg, t, m);
+}
+
+cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, int relaxed, const TileMap *imap)
+{
+    if (relaxed && t.n == 7) return launch_polyexp_mixed<7>(s, I, R, d, nimg, t, imap);
+    if (relaxed && t.n == 5) return launch_polyexp_mixed<5>(s, I, R, d, nimg, t, imap);
     if (t.n == 7 || t.n == 5) {
         dim3 grid((d.w + PF_TW - 1) / PF_TW, (d.h + PF_TH - 1) / PF_TH, nimg);
         if (t.n == 7) {

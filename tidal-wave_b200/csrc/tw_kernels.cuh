@@ -65,7 +65,15 @@ size_t level_image_smem_bytes(int smem_w, int smem_h, int tile_w, int ksize, int
 
 // K2: polynomial expansion I -> R (5 planes), SURVEY App. A.3.  nimg = 2*B images.
 // relaxed = 1: the mixed double/float horizontal pass (polyN 5 / 7 only; otherwise the faithful kernels run).
-cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, int relaxed);
+// `imap` (optional): tensor map of I made by make_polyexp_map -- interior tiles of the relaxed kernel are then staged by ONE TMA tile copy
+// (cp.async.bulk.tensor) instead of per-thread loads; border tiles (replicate clamp) keep the per-thread path.
+struct TileMap {
+    alignas(64) unsigned char opaque[128]; // one CUtensorMap
+    int valid;
+};
+bool make_polyexp_map(const float *I, const LevelDims &d, int nimg, int polyN, TileMap *out);
+cudaError_t launch_polyexp(cudaStream_t s, const float *I, float *R, const LevelDims &d, int nimg, const PolyTables &t, int relaxed,
+                           const TileMap *imap = nullptr);
 
 // K3: (coarse flow -> bilinear upsample * 1/pyrScale | zero) -> first update-matrices, App. A.1 + A.4.
 struct FirstUpdateArgs {

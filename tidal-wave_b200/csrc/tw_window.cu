@@ -760,6 +760,7 @@ cudaError_t launch_strip(cudaStream_t s, const StripMaps &m, const StripArgs &sa
 } // namespace
 
 static_assert(sizeof(CUtensorMap) * 6 <= sizeof(StripMaps::opaque), "StripMaps holds six tensor maps");
+static_assert(sizeof(CUtensorMap) <= sizeof(TileMap::opaque), "TileMap holds one tensor map");
 
 // Tensor maps of one (M buffer, R buffer) pair at one scale: M as [B][h][5*pitch] floats (boxes 192 x {1, 8} and 96 x {1, 8}: rows
 // of a channel-pair plane / of the h2 plane), R as [2B][5h][pitch] floats (boxes 64 x 40 and 72 x 40: 8 rows x 5 channels).
@@ -775,6 +776,18 @@ bool make_strip_maps(const float *M, const float *R, const LevelDims &d, int bat
     if (!encode3(&maps[3], M, 5 * pitch, h, (cuuint64_t)batch, 5 * pitch * 4, 5 * plane * 4, WS_VC, WS_G)) return false;
     if (!encode3(&maps[4], R, pitch, 5 * h, (cuuint64_t)batch * 2, pitch * 4, 5 * plane * 4, WS_SW, 5 * WS_G)) return false;
     if (!encode3(&maps[5], R, pitch, 5 * h, (cuuint64_t)batch * 2, pitch * 4, 5 * plane * 4, WS_R1C, 5 * WS_G)) return false;
+    out->valid = 1;
+    return true;
+}
+
+// Tensor map of the level images I ([nimg][h][pitch] floats) for the poly-exp's staged input tile: box 112 columns x (32 + 2 polyN) rows.
+bool make_polyexp_map(const float *I, const LevelDims &d, int nimg, int polyN, TileMap *out)
+{
+    out->valid = 0;
+    if (d.pitch % 4 != 0 || d.pitch < 112 || polyN < 1 || 32 + 2 * polyN > 256) return false;
+    if (!encode3(reinterpret_cast<CUtensorMap *>(out->opaque), I, (cuuint64_t)d.pitch, (cuuint64_t)d.h, (cuuint64_t)nimg, (cuuint64_t)d.pitch * 4,
+                 (cuuint64_t)d.plane * 4, 112, (cuuint32_t)(32 + 2 * polyN)))
+        return false;
     out->valid = 1;
     return true;
 }
