@@ -166,6 +166,9 @@ const char *tw_last_error(tw_ctx *ctx);
  *                     warp-specialised strip kernel (tw_window.cu: TMA tensor-map rings, register-resident column walkers,
  *                     setmaxnreg).  Same arithmetic, bit-identical results; the strip kernel measures 1-7 % slower (DESIGN.md
  *                     section 4.2), so it is opt-in; TW_WINDOW=strip|tiles in the environment sets the default.
+ *   "plan_cache" = n (default 3; TW_PLAN_CACHE): plans -- the device buffers, tables, tensor maps and the captured graph of one
+ *                     (size, parameters) -- kept besides the current one, least recently used evicted first, all dropped when
+ *                     memory runs out: a dispatcher that sees mixed page sizes does not rebuild a plan on every switch.
  *   "polyexp_tma" = 1: interior input tiles of the relaxed polynomial expansion are staged by one TMA tensor-map copy instead of
  *                     per-thread loads (bit-identical; measured 5 % slower, hence opt-in; TW_POLY_TMA=1 sets the default).
  *   "level_generic", "level_unfused", "tight_pitch", "box_unfused": alternative code paths (also the fall-backs of unusual

@@ -480,3 +480,30 @@ def test_deep_pyramid_long_preblur_levels(tw, oracle, size, levels):
         rc, fx, fy, _ = o.calculateInternal(a, b, tw.OpticalFlowParameter(**kw))
         assert rc == 0 and np.array_equal(fx, ref[..., 0]) and np.array_equal(fy, ref[..., 1]), generic
         o.close()
+
+
+@pytest.mark.gpu
+def test_plan_cache_switching_sizes(tw):
+    """A context keeps the plans (buffers, tables, tensor maps, captured graph) of the sizes it has seen: switching back and forth between
+    page sizes -- what a screenshot directory does -- gives the first-time answers again (graph replay included), also after evictions
+    (more sizes than "plan_cache" holds) and with the cache turned off."""
+    sizes = [(320, 200), (200, 320), (416, 240), (250, 250), (300, 180), (180, 300)]
+    pairs = {sz: tw.synth.make_pair("S", sz[0], sz[1], 7 + i, defect=True) for i, sz in enumerate(sizes)}
+    ref = {}
+    o = tw.OpticalFlow(0, 0, 0, 2)
+    for sz in sizes:
+        rc, fx, fy, _ = o.calculateInternal(*pairs[sz])
+        assert rc == 0
+        ref[sz] = (fx.copy(), fy.copy(), o.calculate(*pairs[sz], threshold=0.5))
+    o.close()
+    for cache in (3, 0):
+        o = tw.OpticalFlow(0, 0, 0, 2)
+        o.set_option("plan_cache", cache)
+        order = [0, 1, 0, 1, 0, 2, 3, 4, 5, 0, 1, 5, 0, 0, 1]
+        for k in order:
+            sz = sizes[k]
+            rc, fx, fy, _ = o.calculateInternal(*pairs[sz])
+            assert rc == 0 and np.array_equal(fx, ref[sz][0]) and np.array_equal(fy, ref[sz][1]), (cache, sz)
+            r = o.calculate(*pairs[sz], threshold=0.5)
+            assert r["status"] == ref[sz][2]["status"] and r["vector"] == ref[sz][2]["vector"]
+        o.close()

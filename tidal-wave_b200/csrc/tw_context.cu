@@ -86,7 +86,19 @@ struct tw_ctx {
     GraphKey graph_key, seen_key;
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_launches = 0;
-    unsigned long long plan_gen = 0;
+    unsigned long long plan_gen = 0, next_gen = 0;
+    // Plans (all device buffers, tables and tensor maps of one (size, parameters)) that are not the current one, each with its
+    // captured graph: screenshot directories mix page sizes, and rebuilding a plan costs tens of cudaMalloc / cudaFree calls.
+    struct PlanSlot {
+        Plan plan;
+        GraphKey graph_key, seen_key;
+        cudaGraphExec_t graph_exec = nullptr;
+        long long graph_launches = 0;
+        unsigned long long gen = 0, last_use = 0;
+    };
+    std::vector<PlanSlot> plan_cache;
+    unsigned long long use_tick = 0;
+    int plan_cache_max = 3; // + the current plan (TW_PLAN_CACHE)
     // results
     int *d_counts = nullptr;
     int *h_counts = nullptr; // pinned
@@ -157,9 +169,44 @@ void drop_graph(tw_ctx *ctx)
 void free_plan(tw_ctx *ctx)
 {
     drop_graph(ctx);
-    ctx->plan_gen++;
+    ctx->plan_gen = ++ctx->next_gen;
     for (void *p : ctx->plan.allocs) cudaFree(p);
     ctx->plan = Plan();
+}
+
+void free_slot(tw_ctx::PlanSlot &s)
+{
+    if (s.graph_exec) cudaGraphExecDestroy(s.graph_exec);
+    for (void *p : s.plan.allocs) cudaFree(p);
+    s = tw_ctx::PlanSlot();
+}
+
+// Frees every cached plan (stream idle): options that change how plans are built, out-of-memory, destruction.
+void flush_plan_cache(tw_ctx *ctx)
+{
+    for (auto &s : ctx->plan_cache) free_slot(s);
+    ctx->plan_cache.clear();
+}
+
+// The current plan (valid or not) leaves ctx->plan: into the cache with its graph, or freed.  Stream idle.
+void stash_plan(tw_ctx *ctx)
+{
+    if (!ctx->plan.valid || ctx->plan_cache_max < 1) { free_plan(ctx); return; }
+    while ((int)ctx->plan_cache.size() >= ctx->plan_cache_max) { // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < ctx->plan_cache.size(); i++)
+            if (ctx->plan_cache[i].last_use < ctx->plan_cache[lru].last_use) lru = i;
+        free_slot(ctx->plan_cache[lru]);
+        ctx->plan_cache.erase(ctx->plan_cache.begin() + lru);
+    }
+    tw_ctx::PlanSlot s;
+    s.plan = std::move(ctx->plan);
+    s.graph_key = ctx->graph_key; s.seen_key = ctx->seen_key; s.graph_exec = ctx->graph_exec; s.graph_launches = ctx->graph_launches;
+    s.gen = ctx->plan_gen; s.last_use = ++ctx->use_tick;
+    ctx->plan_cache.push_back(std::move(s));
+    ctx->plan = Plan();
+    ctx->graph_exec = nullptr; ctx->graph_key = tw_ctx::GraphKey(); ctx->seen_key = tw_ctx::GraphKey(); ctx->graph_launches = 0;
+    ctx->plan_gen = ++ctx->next_gen;
 }
 
 template <typename T>
@@ -167,6 +214,11 @@ bool dev_alloc(tw_ctx *ctx, T **out, size_t count)
 {
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 256);
+    if (e == cudaErrorMemoryAllocation && !ctx->plan_cache.empty()) { // out of memory: the cached plans go first (the stream is idle here)
+        cudaGetLastError();
+        flush_plan_cache(ctx);
+        e = cudaMalloc(&p, count * sizeof(T) + 256);
+    }
     if (e != cudaSuccess) return set_err(ctx, "cudaMalloc", e);
     ctx->plan.allocs.push_back(p);
     *out = reinterpret_cast<T *>(p);
@@ -329,7 +381,17 @@ bool build_plan(tw_ctx *ctx, int W, int H, const tw_flow_param &p)
     if (pl.valid && pl.W == W && pl.H == H && pl.batch == ctx->max_batch && pl.keep == ctx->keep_levels && same_param(pl.p, p))
         return true;
     CK(cudaStreamSynchronize(ctx->stream));
-    free_plan(ctx);
+    stash_plan(ctx);
+    for (size_t i = 0; i < ctx->plan_cache.size(); i++) { // a plan of this size and these parameters from before?
+        tw_ctx::PlanSlot &s = ctx->plan_cache[i];
+        if (s.plan.valid && s.plan.W == W && s.plan.H == H && s.plan.batch == ctx->max_batch && s.plan.keep == ctx->keep_levels && same_param(s.plan.p, p)) {
+            ctx->plan = std::move(s.plan);
+            ctx->graph_key = s.graph_key; ctx->seen_key = s.seen_key; ctx->graph_exec = s.graph_exec; ctx->graph_launches = s.graph_launches;
+            ctx->plan_gen = s.gen;
+            ctx->plan_cache.erase(ctx->plan_cache.begin() + i);
+            return true;
+        }
+    }
     pl.W = W; pl.H = H; pl.p = p; pl.batch = ctx->max_batch; pl.keep = ctx->keep_levels;
     const int B = pl.batch;
 
@@ -774,6 +836,7 @@ tw_ctx *tw_create(int device, int max_w, int max_h, int max_batch, char *err, in
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch < 1 ? 1 : max_batch;
     ctx->opt_arith = default_arith();
     if (const char *g = getenv("TW_GRAPH")) ctx->opt_graph = atoi(g) ? 1 : 0; // TW_GRAPH=0: eager launches (profilers)
+    if (const char *g = getenv("TW_PLAN_CACHE")) ctx->plan_cache_max = atoi(g) < 0 ? 0 : atoi(g);
     if (const char *g = getenv("TW_POLY_TMA")) ctx->opt_poly_no_tma = atoi(g) ? 0 : 1;
     if (const char *g = getenv("TW_WINDOW")) ctx->opt_window_tiles = !strcmp(g, "strip") ? 0 : 1; // TW_WINDOW=strip|tiles
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(cudaGetErrorString(e)); }
@@ -794,6 +857,7 @@ void tw_destroy(tw_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drain_profile(ctx);
     free_plan(ctx);
+    flush_plan_cache(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -1277,13 +1341,27 @@ int tw_set_option(tw_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "polyexp_tma")) { // takes effect when the next plan is built (the tensor maps are made with the plan)
         ctx->opt_poly_no_tma = value ? 0 : 1;
         ctx->plan.valid = false;
+        cudaStreamSynchronize(ctx->stream);
+        flush_plan_cache(ctx);
         return TW_OK;
     }
     if (!strcmp(name, "box_unfused")) { ctx->opt_box_unfused = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "window_tiles")) { ctx->opt_window_tiles = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_generic")) { ctx->opt_level_generic = value ? 1 : 0; return TW_OK; }
     if (!strcmp(name, "level_unfused")) { ctx->opt_level_unfused = value ? 1 : 0; return TW_OK; }
-    if (!strcmp(name, "tight_pitch")) { ctx->opt_tight_pitch = value ? 1 : 0; ctx->plan.valid = false; return TW_OK; }
+    if (!strcmp(name, "tight_pitch")) {
+        ctx->opt_tight_pitch = value ? 1 : 0;
+        ctx->plan.valid = false;
+        cudaStreamSynchronize(ctx->stream);
+        flush_plan_cache(ctx);
+        return TW_OK;
+    }
+    if (!strcmp(name, "plan_cache")) { // how many plans besides the current one are kept (0: rebuild on every change of size / parameters)
+        ctx->plan_cache_max = value < 0 ? 0 : value;
+        cudaStreamSynchronize(ctx->stream);
+        flush_plan_cache(ctx);
+        return TW_OK;
+    }
     ctx->err = std::string("unknown option ") + name;
     return TW_BAD_PARAMETER;
 }
