@@ -17,6 +17,9 @@
 
 #include <cstdint>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <vector>
 
 namespace {
@@ -25,13 +28,16 @@ const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-constexpr int kLookBits = 9;
+constexpr int kLookBits = 10;
 
 struct Huff {
     bool present = false;
     int mincode[17], maxcode[18], valptr[17];
     uint8_t vals[256];
     uint16_t look[1 << kLookBits]; // (length << 8) | symbol for codes of at most kLookBits bits, 0 = longer code
+    // AC tables: where the code AND the magnitude bits that follow it fit in kLookBits bits, the decoded coefficient itself:
+    // (value << 8) | (run << 4) | total bits; 0 = take the two-step path (value in [-128, 127], never 0 for a coefficient)
+    int16_t fast_ac[1 << kLookBits];
     void build(const uint8_t *bits /* [1..16] */, const uint8_t *v, int n)
     {
         memset(vals, 0, sizeof vals);
@@ -53,6 +59,14 @@ struct Huff {
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
+        for (int i = 0; i < (1 << kLookBits); i++) {
+            fast_ac[i] = 0;
+            const int e = look[i], len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
+            if (!e || !mag || len + mag > kLookBits) continue;
+            int v = ((i << len) & ((1 << kLookBits) - 1)) >> (kLookBits - mag); // the mag bits after the code
+            if (v < (1 << (mag - 1))) v += 1 - (1 << mag);                     // T.81 F.2.2.1 EXTEND
+            if (v >= -128 && v <= 127) fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+        }
         present = true;
     }
 };
@@ -66,6 +80,9 @@ struct Component {
     std::vector<int16_t> coef;  // [hpad][wpad][64], natural (row-major) order -- only kept for the luma component
 };
 
+const uint16_t kEndianProbe0 = 1;
+const bool kLittleEndianHost = *reinterpret_cast<const uint8_t *>(&kEndianProbe0) == 1;
+
 struct BitReader {
     const uint8_t *p, *end;
     uint64_t buf = 0; // bits left-aligned
@@ -74,6 +91,20 @@ struct BitReader {
     BitReader(const uint8_t *b, const uint8_t *e) : p(b), end(e) {}
     void fill()
     {
+        if (!hit_marker && end - p >= 8 && cnt <= 56) { // eight bytes at once when none of them is 0xFF (stuffing / marker)
+            uint64_t w;
+            memcpy(&w, p, 8);
+            w = __builtin_bswap64(w); // little-endian host (checked by kLittleEndian below; big-endian takes the byte loop)
+            const uint64_t x = ~w;
+            if (kLittleEndianHost && !((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull)) {
+                const int nb = (64 - cnt) >> 3;
+                const uint64_t m = nb == 8 ? ~0ull : ~(~0ull >> (nb * 8));
+                buf |= (w & m) >> cnt;
+                cnt += nb * 8;
+                p += nb;
+                return;
+            }
+        }
         while (cnt <= 56) {
             int c = 0;
             if (!hit_marker && p < end) {
@@ -117,12 +148,16 @@ int decode_symbol(BitReader &br, const Huff &h)
 {
     const int e = h.look[br.peek(kLookBits)];
     if (e) { br.skip(e >> 8); return e & 255; }
-    int code = br.bit(), l = 1;
-    while (code > h.maxcode[l]) {
-        if (++l > 16) return 0; // corrupt data: libjpeg warns and returns 0
-        code = (code << 1) | br.bit();
+    const int code16 = br.peek(16); // canonical codes: the first length whose largest code is not below the prefix
+    for (int l = 1; l <= 16; l++) {
+        const int code = code16 >> (16 - l);
+        if (code <= h.maxcode[l]) {
+            br.skip(l);
+            return h.vals[(h.valptr[l] + code - h.mincode[l]) & 255];
+        }
     }
-    return h.vals[(h.valptr[l] + code - h.mincode[l]) & 255];
+    br.skip(16);
+    return 0; // corrupt data: libjpeg warns and returns 0
 }
 
 // ---- inverse DCT, "ISLOW" ----
@@ -206,6 +241,104 @@ void idct_islow(const int16_t *in, const uint16_t *q, uint8_t *out, int stride)
     }
 }
 
+// The same inverse DCT on eight 32-bit lanes (AVX2; pass 1: lane = column, pass 2: lane = row).  Integer arithmetic is exact
+// as long as nothing overflows, so wherever every dequantised coefficient and every pass-1 output lies within +-8191 (any
+// block a real encoder produces: pass-1 outputs of 8-bit samples stay below 4096 * 1.5) the int32 lanes hold exactly the
+// int64 values of idct_islow above; otherwise -- and on a host without AVX2 -- the function declines and the caller runs
+// the scalar form.
+#if defined(__x86_64__)
+#define TW_JPEG_AVX2 1
+#define TW_AVX2 __attribute__((target("avx2")))
+
+TW_AVX2 inline void islow_lanes(const __m256i *in, __m256i *out, int shift)
+{
+#define K(c) _mm256_set1_epi32(c)
+#define MUL(a, c) _mm256_mullo_epi32(a, K(c))
+#define ADD _mm256_add_epi32
+#define SUB _mm256_sub_epi32
+    __m256i z2 = in[2], z3 = in[6];
+    __m256i z1 = MUL(ADD(z2, z3), 4433);
+    __m256i tmp2 = SUB(z1, MUL(z3, 15137)), tmp3 = ADD(z1, MUL(z2, 6270));
+    __m256i tmp0 = _mm256_slli_epi32(ADD(in[0], in[4]), kConstBits), tmp1 = _mm256_slli_epi32(SUB(in[0], in[4]), kConstBits);
+    const __m256i tmp10 = ADD(tmp0, tmp3), tmp13 = SUB(tmp0, tmp3), tmp11 = ADD(tmp1, tmp2), tmp12 = SUB(tmp1, tmp2);
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = ADD(tmp0, tmp3); z2 = ADD(tmp1, tmp2); z3 = ADD(tmp0, tmp2);
+    __m256i z4 = ADD(tmp1, tmp3);
+    const __m256i z5 = MUL(ADD(z3, z4), 9633);
+    tmp0 = MUL(tmp0, 2446); tmp1 = MUL(tmp1, 16819); tmp2 = MUL(tmp2, 25172); tmp3 = MUL(tmp3, 12299);
+    z1 = MUL(z1, -7373); z2 = MUL(z2, -20995); z3 = ADD(MUL(z3, -16069), z5); z4 = ADD(MUL(z4, -3196), z5);
+    tmp0 = ADD(tmp0, ADD(z1, z3)); tmp1 = ADD(tmp1, ADD(z2, z4)); tmp2 = ADD(tmp2, ADD(z2, z3)); tmp3 = ADD(tmp3, ADD(z1, z4));
+    const __m256i rnd = K(1 << (shift - 1));
+    const __m128i sh = _mm_cvtsi32_si128(shift);
+#define OUT(a, op, b) _mm256_sra_epi32(ADD(op(a, b), rnd), sh)
+    out[0] = OUT(tmp10, ADD, tmp3); out[7] = OUT(tmp10, SUB, tmp3);
+    out[1] = OUT(tmp11, ADD, tmp2); out[6] = OUT(tmp11, SUB, tmp2);
+    out[2] = OUT(tmp12, ADD, tmp1); out[5] = OUT(tmp12, SUB, tmp1);
+    out[3] = OUT(tmp13, ADD, tmp0); out[4] = OUT(tmp13, SUB, tmp0);
+#undef OUT
+#undef K
+#undef MUL
+#undef ADD
+#undef SUB
+}
+
+TW_AVX2 inline void transpose8(const __m256i *r, __m256i *o)
+{
+    const __m256i t0 = _mm256_unpacklo_epi32(r[0], r[1]), t1 = _mm256_unpackhi_epi32(r[0], r[1]);
+    const __m256i t2 = _mm256_unpacklo_epi32(r[2], r[3]), t3 = _mm256_unpackhi_epi32(r[2], r[3]);
+    const __m256i t4 = _mm256_unpacklo_epi32(r[4], r[5]), t5 = _mm256_unpackhi_epi32(r[4], r[5]);
+    const __m256i t6 = _mm256_unpacklo_epi32(r[6], r[7]), t7 = _mm256_unpackhi_epi32(r[6], r[7]);
+    const __m256i u0 = _mm256_unpacklo_epi64(t0, t2), u1 = _mm256_unpackhi_epi64(t0, t2);
+    const __m256i u2 = _mm256_unpacklo_epi64(t1, t3), u3 = _mm256_unpackhi_epi64(t1, t3);
+    const __m256i u4 = _mm256_unpacklo_epi64(t4, t6), u5 = _mm256_unpackhi_epi64(t4, t6);
+    const __m256i u6 = _mm256_unpacklo_epi64(t5, t7), u7 = _mm256_unpackhi_epi64(t5, t7);
+    o[0] = _mm256_permute2x128_si256(u0, u4, 0x20); o[1] = _mm256_permute2x128_si256(u1, u5, 0x20);
+    o[2] = _mm256_permute2x128_si256(u2, u6, 0x20); o[3] = _mm256_permute2x128_si256(u3, u7, 0x20);
+    o[4] = _mm256_permute2x128_si256(u0, u4, 0x31); o[5] = _mm256_permute2x128_si256(u1, u5, 0x31);
+    o[6] = _mm256_permute2x128_si256(u2, u6, 0x31); o[7] = _mm256_permute2x128_si256(u3, u7, 0x31);
+}
+
+TW_AVX2 bool idct_islow_avx2(const int16_t *in, const uint16_t *q, uint8_t *out, int stride)
+{
+    __m256i a[8], w[8];
+    const __m256i big = _mm256_set1_epi32(~8191);
+    __m256i m = _mm256_setzero_si256();
+    for (int k = 0; k < 8; k++) {
+        a[k] = _mm256_mullo_epi32(_mm256_cvtepi16_epi32(_mm_loadu_si128((const __m128i *)(in + 8 * k))),
+                                  _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i *)(q + 8 * k))));
+        m = _mm256_or_si256(m, _mm256_abs_epi32(a[k]));
+    }
+    if (!_mm256_testz_si256(m, big)) return false;
+    islow_lanes(a, w, kConstBits - kPass1Bits); // w[r] = row r of the workspace, lane = column
+    m = _mm256_abs_epi32(w[0]);
+    for (int r = 1; r < 8; r++) m = _mm256_or_si256(m, _mm256_abs_epi32(w[r]));
+    if (!_mm256_testz_si256(m, big)) return false;
+    transpose8(w, a);                           // a[k] = workspace column k, lane = row
+    islow_lanes(a, w, kConstBits + kPass1Bits + 3); // w[c] = output column c, lane = row
+    transpose8(w, a);                           // a[r] = output row r
+    // the wrap-around range-limit table = ((v mod 1024, as a signed 10-bit number) + 128) clamped to a byte
+    const __m256i c128 = _mm256_set1_epi32(128);
+    for (int r = 0; r < 8; r += 2) {
+        const __m256i v0 = _mm256_add_epi32(_mm256_srai_epi32(_mm256_slli_epi32(a[r], 22), 22), c128);
+        const __m256i v1 = _mm256_add_epi32(_mm256_srai_epi32(_mm256_slli_epi32(a[r + 1], 22), 22), c128);
+        const __m256i p16 = _mm256_packs_epi32(v0, v1);    // per 128-bit half: row r cols 0-3 | row r+1 cols 0-3 ; cols 4-7 likewise
+        const __m256i p8 = _mm256_packus_epi16(p16, p16);  // bytes: [r c0-3][r+1 c0-3][..][..] | [r c4-7][r+1 c4-7][..][..]
+        const __m128i lo = _mm256_castsi256_si128(p8), hi = _mm256_extracti128_si256(p8, 1);
+        const __m128i rows = _mm_unpacklo_epi32(lo, hi);   // [r c0-3][r c4-7][r+1 c0-3][r+1 c4-7]
+        _mm_storel_epi64((__m128i *)(out + (size_t)r * stride), rows);
+        _mm_storel_epi64((__m128i *)(out + (size_t)(r + 1) * stride), _mm_srli_si128(rows, 8));
+    }
+    return true;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+inline bool idct_islow_lanes(const int16_t *in, const uint16_t *q, uint8_t *out, int stride)
+{
+    return kHaveAvx2 && idct_islow_avx2(in, q, out, stride);
+}
+#else
+inline bool idct_islow_lanes(const int16_t *, const uint16_t *, uint8_t *, int) { return false; }
+#endif
+
 struct Decoder {
     const uint8_t *b;
     size_t n;
@@ -219,31 +352,44 @@ struct Decoder {
     Component comp[4];
     int luma = 0;
     int eobrun = 0;
+    uint8_t *out_ = nullptr;   // baseline files: every luma block goes through the inverse DCT as soon as it is decoded
+    bool luma_scanned = false; // (no coefficient store; a block is coded exactly once)
 
     uint16_t be16(size_t pos) const { return (uint16_t)((b[pos] << 8) | b[pos + 1]); }
 
     int16_t *block(Component &c, int bx, int by) { return c.coef.data() + ((size_t)by * c.wpad + bx) * 64; }
 
     // ---- per-block entropy decoding; `blk` == nullptr: decode and discard (chroma) ----
-    void baseline_block(BitReader &br, Component &c, int16_t *blk)
+    // returns the zigzag index of the last coefficient stored (0 = DC only)
+    int baseline_block(BitReader &br, Component &c, int16_t *blk)
     {
         int s = decode_symbol(br, dc[c.dc_tbl]);
         int diff = s ? extend(br.bits(s), s) : 0;
         c.last_dc += diff;
         if (blk) blk[0] = (int16_t)c.last_dc;
         const Huff &h = ac[c.ac_tbl];
+        int last = 0;
         for (int k = 1; k < 64; k++) {
+            if (br.cnt < 32) br.fill(); // one refill covers a code (<= 16 bits) and its magnitude bits (<= 15)
+            const int idx = (int)(br.buf >> (64 - kLookBits)), f = h.fast_ac[idx];
+            if (f) { // code + magnitude resolved by one lookup
+                k += (f >> 4) & 15;
+                br.skip(f & 15);
+                if (blk && k < 64) { blk[kZigzag[k]] = (int16_t)(f >> 8); last = k; }
+                continue;
+            }
             int rs = decode_symbol(br, h), r = rs >> 4;
             s = rs & 15;
             if (s) {
                 k += r;
                 int v = extend(br.bits(s), s);
-                if (blk && k < 64) blk[kZigzag[k]] = (int16_t)v;
+                if (blk && k < 64) { blk[kZigzag[k]] = (int16_t)v; last = k; }
             } else {
                 if (r != 15) break;
                 k += 15;
             }
         }
+        return last;
     }
     void dc_first(BitReader &br, Component &c, int16_t *blk, int Al)
     {
@@ -348,10 +494,20 @@ struct Decoder {
         }
         eobrun = 0;
         BitReader br(b + seg_begin, b + e);
+        luma_scanned = true;
+        const uint16_t *lq = qt[comp[luma].tq];
+        if (!progressive && !have_qt[comp[luma].tq]) return TW_BAD_IMAGE_FORMAT;
         auto one_block = [&](Component &c, int bx, int by) {
+            if (!progressive) {
+                if (&c != &comp[luma] || bx >= c.wblk || by >= c.hblk) { baseline_block(br, c, nullptr); return; }
+                alignas(32) int16_t cf[64];
+                memset(cf, 0, sizeof cf);
+                const int last = baseline_block(br, c, cf);
+                emit_block(cf, last == 0, lq, bx, by);
+                return;
+            }
             int16_t *blk = (&c == &comp[luma]) ? block(c, bx, by) : nullptr;
-            if (!progressive) baseline_block(br, c, blk);
-            else if (Ss == 0) { if (Ah == 0) dc_first(br, c, blk, Al); else dc_refine(br, blk, Al); }
+            if (Ss == 0) { if (Ah == 0) dc_first(br, c, blk, Al); else dc_refine(br, blk, Al); }
             else if (Ah == 0) ac_first(br, c, blk, Ss, Se, Al);
             else ac_refine(br, c, blk, Ss, Se, Al);
         };
@@ -485,35 +641,51 @@ struct Decoder {
         *w = W; *h = H;
         if (!out) return TW_OK;
         if (cap < (size_t)W * H) return TW_BAD_PARAMETER;
-        comp[luma].coef.assign((size_t)comp[luma].wpad * comp[luma].hpad * 64, 0);
+        out_ = out;
+        if (progressive) comp[luma].coef.assign((size_t)comp[luma].wpad * comp[luma].hpad * 64, 0);
         return TW_OK;
+    }
+
+    // inverse DCT of one luma block into the output image (clipped at the right / bottom edge)
+    void emit_block(const int16_t *blk, bool dc_only, const uint16_t *q, int bx, int by)
+    {
+        const int ys = by * 8, xs = bx * 8;
+        const bool inside = xs + 8 <= W && ys + 8 <= H;
+        uint8_t px[64];
+        uint8_t *dst = inside ? out_ + (size_t)ys * W + xs : px;
+        const int stride = inside ? W : 8;
+        if (dc_only) {
+            // DC-only block (most of a screenshot): both passes of the inverse DCT take their zero-AC shortcuts, the block is
+            // the constant range_limit(descale(dc * q0 << PASS1_BITS, PASS1_BITS + 3)) -- same value, 64 multiplies saved
+            const int64_t dc = (int64_t)((int32_t)blk[0] * q[0]) * (1 << kPass1Bits);
+            const uint8_t v = kRange.t[descale(dc, kPass1Bits + 3) & 1023];
+            for (int y = 0; y < 8; y++) memset(dst + (size_t)y * stride, v, 8);
+        } else if (!idct_islow_lanes(blk, q, dst, stride)) {
+            idct_islow(blk, q, dst, stride);
+        }
+        if (!inside)
+            for (int y = 0; y < 8 && ys + y < H; y++) {
+                const int cols = W - xs < 8 ? W - xs : 8;
+                memcpy(out_ + (size_t)(ys + y) * W + xs, px + 8 * y, cols);
+            }
     }
 
     int finish(uint8_t *out)
     {
         Component &c = comp[luma];
         if (!have_qt[c.tq]) return TW_BAD_IMAGE_FORMAT;
-        uint8_t px[64];
+        if (!progressive) {
+            if (!luma_scanned) memset(out, 128, (size_t)W * H); // no luma scan at all: all-zero coefficients
+            return TW_OK;
+        }
         for (int by = 0; by < c.hblk; by++) {
             for (int bx = 0; bx < c.wblk; bx++) {
                 const int16_t *blk = block(c, bx, by);
-                // DC-only block (most of a screenshot): both passes of the inverse DCT take their zero-AC shortcuts, the block is
-                // the constant range_limit(descale(dc * q0 << PASS1_BITS, PASS1_BITS + 3)) -- same value, 64 multiplies saved
                 uint64_t ac[16];
                 memcpy(ac, blk, sizeof ac);
                 uint64_t any = ac[0] & ~(uint64_t)0xFFFF; // little-endian: coefficient 0 is the low half-word
                 for (int i = 1; i < 16; i++) any |= ac[i];
-                if (!any && kLittleEndian) {
-                    const int64_t dc = (int64_t)((int32_t)blk[0] * qt[c.tq][0]) * (1 << kPass1Bits);
-                    memset(px, kRange.t[descale(dc, kPass1Bits + 3) & 1023], 64);
-                } else {
-                    idct_islow(blk, qt[c.tq], px, 8);
-                }
-                const int ys = by * 8, xs = bx * 8;
-                for (int y = 0; y < 8 && ys + y < H; y++) {
-                    const int cols = W - xs < 8 ? W - xs : 8;
-                    memcpy(out + (size_t)(ys + y) * W + xs, px + 8 * y, cols);
-                }
+                emit_block(blk, !any && kLittleEndian, qt[c.tq], bx, by);
             }
         }
         return TW_OK;
