@@ -76,8 +76,8 @@ const char *tw_version(void);
 /* Number of CUDA devices visible (cv::gpu::getCudaEnabledDeviceCount, src/consumer.cpp:19-20). */
 int tw_device_count(void);
 
-/* cv::imread(path, IMREAD_GRAYSCALE) on an in-memory file (src/opticalflow.cpp:37,44): PNG (non-interlaced, 8-bit; colour ->
- * gray exactly as OpenCV/libpng: (9797 R + 19234 G + 3737 B) >> 15), JPEG (baseline / progressive Huffman, gray or YCbCr: the
+/* cv::imread(path, IMREAD_GRAYSCALE) on an in-memory file (src/opticalflow.cpp:37,44): PNG (every colour type and bit depth, Adam7
+ * or not, critical-chunk CRCs checked; colour -> gray exactly as OpenCV/libpng: (9797 R + 19234 G + 3737 B) >> 15), JPEG (baseline / progressive Huffman, gray or YCbCr: the
  * luma plane through libjpeg's ISLOW inverse DCT, as OpenCV's JCS_GRAYSCALE request does; EXIF orientation ignored like
  * OpenCV 2.4.9) and binary PGM.  Host code, no device needed.  Call with out == NULL to query *w, *h.  Anything else ->
  * TW_BAD_IMAGE_FORMAT, reported by callers as "Can't open <path>". */

@@ -176,3 +176,166 @@ def test_decode_fuzz_sanitizers(tmp_path):
     out = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "runs" in out.stdout
+
+
+def _png_bytes(samples, ctype, depth, interlace, rng, palette=None, trns=None, filters=None):
+    """A PNG file of the H x W x C integer samples (< 2**depth), written here so that every colour type / bit depth / Adam7 /
+    row filter the format has can be put in front of the decoder (cv2.imwrite only writes a few of them)."""
+    import struct
+    import zlib
+    H, W, C = samples.shape
+    bits = C * depth
+    bpp = max(1, bits // 8)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    def pack_rows(img):
+        h, w, _ = img.shape
+        flat = img.reshape(h, w * C)
+        if depth == 16:
+            return np.stack([flat >> 8, flat & 255], -1).reshape(h, -1).astype(np.uint8)
+        if depth == 8:
+            return flat.astype(np.uint8)
+        per = 8 // depth
+        pad = (-flat.shape[1]) % per
+        flat = np.pad(flat, ((0, 0), (0, pad)))
+        out = np.zeros((h, flat.shape[1] // per), np.int64)
+        for k in range(per):
+            out |= flat[:, k::per] << ((per - 1 - k) * depth)
+        return out.astype(np.uint8)
+
+    def filt(rows):
+        out = bytearray()
+        prev = np.zeros(rows.shape[1], np.int64)
+        for y in range(rows.shape[0]):
+            cur = rows[y].astype(np.int64)
+            f = int(rng.integers(0, 5)) if filters is None else filters
+            a = np.concatenate([np.zeros(bpp, np.int64), cur[:-bpp]]) if cur.size > bpp else np.zeros_like(cur)
+            if cur.size <= bpp:
+                a = np.zeros_like(cur)
+            c = np.concatenate([np.zeros(bpp, np.int64), prev[:-bpp]]) if cur.size > bpp else np.zeros_like(cur)
+            if f == 0:
+                pred = 0
+            elif f == 1:
+                pred = a
+            elif f == 2:
+                pred = prev
+            elif f == 3:
+                pred = (a + prev) >> 1
+            else:
+                pp = a + prev - c
+                pa, pb, pc = np.abs(pp - a), np.abs(pp - prev), np.abs(pp - c)
+                pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+            out.append(f)
+            out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+            prev = cur
+        return bytes(out)
+
+    if interlace:
+        passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+    else:
+        passes = [(0, 0, 1, 1)]
+    raw = b""
+    for x0, y0, dx, dy in passes:
+        sub = samples[y0::dy, x0::dx]
+        if sub.shape[0] and sub.shape[1]:
+            raw += filt(pack_rows(sub))
+    comp = zlib.compress(raw, 6)
+    cut = len(comp) // 2
+    body = chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        body += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    if trns is not None:
+        body += chunk(b"tRNS", trns)
+    body += chunk(b"IDAT", comp[:cut]) + chunk(b"IDAT", comp[cut:]) + chunk(b"IEND", b"")
+    return b"\x89PNG\r\n\x1a\n" + body
+
+
+def _png_expected_gray(samples, ctype, depth, palette):
+    """What cv2.imread(IMREAD_GRAYSCALE) makes of those samples (tw_decode.cpp's header comment), restated in NumPy."""
+    s = samples.astype(np.int64)
+    if ctype == 3:
+        rgb = palette.astype(np.int64)[s[..., 0]]
+        return ((9797 * rgb[..., 0] + 19234 * rgb[..., 1] + 3737 * rgb[..., 2]) >> 15).astype(np.uint8)
+    if ctype in (0, 4):
+        g = s[..., 0]
+        return (g >> 8 if depth == 16 else g * (255 // ((1 << depth) - 1))).astype(np.uint8)
+    r, g, b = s[..., 0], s[..., 1], s[..., 2]
+    if depth == 16:
+        return (((9797 * r + 19234 * g + 3737 * b + 16384) >> 15) >> 8).astype(np.uint8)
+    return ((9797 * r + 19234 * g + 3737 * b) >> 15).astype(np.uint8)
+
+
+def test_decode_png_every_type_depth_interlace(tw):
+    """Every (colour type, bit depth) pair of the PNG format, Adam7-interlaced or not, random row filters, ragged sizes (1-pixel and
+    sub-8 widths leave Adam7 passes empty): equal to the NumPy restatement of OpenCV's conversion, and to cv2 itself when importable."""
+    import ctypes as C
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    lib = tw.load()
+    rng = np.random.default_rng(23)
+    combos = [(0, d) for d in (1, 2, 4, 8, 16)] + [(2, 8), (2, 16)] + [(3, d) for d in (1, 2, 4, 8)] + [(4, 8), (4, 16), (6, 8), (6, 16)]
+    sizes = [(1, 1), (1, 9), (7, 3), (8, 8), (13, 21), (33, 50), (64, 37)]
+    nchan = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
+    checked = 0
+    for ctype, depth in combos:
+        for interlace in (0, 1):
+            for (h, w) in sizes:
+                samples = rng.integers(0, 1 << depth, (h, w, nchan[ctype]))
+                palette = rng.integers(0, 256, (1 << depth, 3)) if ctype == 3 else None
+                trns = None
+                if rng.integers(0, 2):  # transparency information must not change the gray output
+                    if ctype == 3:
+                        trns = rng.integers(0, 256, int(rng.integers(1, (1 << depth) + 1)), dtype=np.uint8).tobytes()
+                    elif ctype == 0:
+                        trns = int(rng.integers(0, 1 << depth)).to_bytes(2, "big")
+                    elif ctype == 2:
+                        trns = b"".join(int(v).to_bytes(2, "big") for v in rng.integers(0, 1 << depth, 3))
+                data = _png_bytes(samples, ctype, depth, interlace, rng, palette, trns)
+                want = _png_expected_gray(samples, ctype, depth, palette)
+                ww, hh = C.c_int(), C.c_int()
+                out = np.empty((h, w), np.uint8)
+                rc = lib.tw_decode_gray(data, len(data), out.ctypes.data, out.size, C.byref(ww), C.byref(hh))
+                assert rc == 0 and (hh.value, ww.value) == (h, w), (ctype, depth, interlace, h, w, rc)
+                assert np.array_equal(out, want), (ctype, depth, interlace, h, w)
+                if cv2 is not None:
+                    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+                    assert ref is not None and np.array_equal(out, ref), ("cv2", ctype, depth, interlace, h, w)
+                checked += 1
+    assert checked == len(combos) * 2 * len(sizes)
+
+
+def test_decode_png_rejects_damaged_streams(tw):
+    """A wrong CRC on a critical chunk, a truncated IDAT stream and an unknown filter type fail like libpng's read does (the
+    callers turn that into "Can't open <path>"); data after the last scanline is tolerated (libpng: a warning)."""
+    import ctypes as C
+    import struct
+    import zlib
+    lib = tw.load()
+    rng = np.random.default_rng(3)
+    samples = rng.integers(0, 256, (9, 11, 3))
+    good = _png_bytes(samples, 2, 8, 0, rng)
+    out = np.empty((9, 11), np.uint8)
+    ww, hh = C.c_int(), C.c_int()
+
+    def rc(data):
+        return lib.tw_decode_gray(data, len(data), out.ctypes.data, out.size, C.byref(ww), C.byref(hh))
+    assert rc(good) == 0
+    i = good.index(b"IDAT")
+    bad_crc = bytearray(good)
+    bad_crc[i + 6] ^= 0x40
+    assert rc(bytes(bad_crc)) != 0
+    # rebuild the file around a modified raw stream
+    def rebuild(raw):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+        return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 11, 9, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw))
+                + chunk(b"IEND", b""))
+    raw = b"".join(b"\x00" + samples[y].astype(np.uint8).tobytes() for y in range(9))
+    assert rc(rebuild(raw)) == 0
+    assert rc(rebuild(raw[:-5])) != 0                 # not enough image data
+    assert rc(rebuild(raw + b"\x00" * 40)) == 0       # too much: ignored
+    assert rc(rebuild(b"\x07" + raw[1:])) != 0        # filter type 7 does not exist

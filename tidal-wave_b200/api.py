@@ -143,7 +143,7 @@ def declared_symbols() -> list[str]:
 def imread_gray(path: str):
     """cv::imread(path, IMREAD_GRAYSCALE) (/root/reference/src/opticalflow.cpp:37,44) through tw_decode_gray: PNG / JPEG / PGM.
     Returns None (an "empty Mat") for a missing file or a format this build cannot decode bit-exactly (e.g. CMYK or
-    arithmetic-coded JPEG, interlaced or 16-bit PNG)."""
+    arithmetic-coded JPEG)."""
     try:
         data = open(path, "rb").read()
     except OSError:

@@ -1,8 +1,10 @@
 // tw_decode.cpp -- cv::imread(path, IMREAD_GRAYSCALE) for the formats this build can decode bit-exactly
 // (/root/reference/src/opticalflow.cpp:37,44).
 //
-//   PNG  non-interlaced, 8 bits per sample, colour types 0 (gray), 2 (RGB), 3 (palette), 4 (gray+alpha), 6 (RGBA).
-//        zlib inflate + the five PNG row filters; alpha is dropped; colour -> gray exactly as OpenCV's decoder does
+//   PNG  every colour type (gray, RGB, palette, gray+alpha, RGBA) at every bit depth the format allows (1 / 2 / 4 / 8 / 16),
+//        Adam7-interlaced or not; critical-chunk CRCs are checked.
+//        zlib inflate + the five PNG row filters; alpha / tRNS is dropped; gray below 8 bits is scaled to 0..255; 16-bit samples
+//        keep their high byte (16-bit RGB is weighted at 16 bits first, with rounding); colour -> gray exactly as OpenCV's decoder does
 //        it through libpng (png_set_rgb_to_gray with 0.299 / 0.587): gray = (9797*R + 19234*G + 3737*B) >> 15,
 //        truncating (libpng turns 0.299 / 0.587 into the integers 29900*32768/100000 and 58700*32768/100000).  Verified bit-identical to cv2.imread(..., IMREAD_GRAYSCALE) on the reference's PNG fixtures.
 //   PGM  binary P5, maxval 255.
@@ -19,12 +21,6 @@
 namespace {
 
 uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
-
-int paeth(int a, int b, int c)
-{
-    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
-    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-}
 
 int decode_pgm(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int *h)
 {
@@ -53,78 +49,242 @@ int decode_pgm(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int
     return TW_OK;
 }
 
+// ---- PNG ----
+// Undo the filter of one scanline in place (PNG spec 9.2).  B = bytes per pixel (1 for sub-byte depths); prev = the unfiltered
+// line above, or nullptr for the first line of an image / pass (all zero).  The left neighbour a and the upper-left c of each of
+// the B byte lanes live in registers: going through line[i - B] would put a store-to-load forward on every byte's critical path.
+template <int B> bool unfilter_line(int f, uint8_t *line, const uint8_t *prev, size_t n)
+{
+    uint8_t a[B], c[B];
+    for (int k = 0; k < B; k++) a[k] = c[k] = 0;
+    size_t i = 0;
+    switch (f) {
+        case 0: return true;
+        case 1:
+            for (; i + B <= n; i += B)
+                for (int k = 0; k < B; k++) line[i + k] = a[k] = (uint8_t)(line[i + k] + a[k]);
+            for (int k = 0; i < n; i++, k++) line[i] = (uint8_t)(line[i] + a[k]);
+            return true;
+        case 2:
+            if (prev) for (; i < n; i++) line[i] = (uint8_t)(line[i] + prev[i]);
+            return true;
+        case 3:
+            for (; i + B <= n; i += B)
+                for (int k = 0; k < B; k++) line[i + k] = a[k] = (uint8_t)(line[i + k] + ((a[k] + (prev ? prev[i + k] : 0)) >> 1));
+            for (int k = 0; i < n; i++, k++) line[i] = (uint8_t)(line[i] + ((a[k] + (prev ? prev[i] : 0)) >> 1));
+            return true;
+        case 4:
+            if (!prev) return unfilter_line<B>(1, line, prev, n); // b = c = 0: the predictor is a
+            for (; i + B <= n; i += B)
+                for (int k = 0; k < B; k++) {
+                    const int av = a[k], bv = prev[i + k], cv = c[k];
+                    const int pa0 = bv - cv, pb0 = av - cv; // p - a, p - b with p = a + b - c
+                    const int pa = abs(pa0), pb = abs(pb0), pc = abs(pa0 + pb0);
+                    const int pred = (pa <= pb && pa <= pc) ? av : (pb <= pc ? bv : cv);
+                    c[k] = (uint8_t)bv;
+                    line[i + k] = a[k] = (uint8_t)(line[i + k] + pred);
+                }
+            for (int k = 0; i < n; i++, k++) { // a partial last pixel cannot occur in a valid stream; keep the bytes defined
+                const int av = a[k], bv = prev[i], cv = c[k];
+                const int pa0 = bv - cv, pb0 = av - cv;
+                const int pa = abs(pa0), pb = abs(pb0), pc = abs(pa0 + pb0);
+                line[i] = (uint8_t)(line[i] + ((pa <= pb && pa <= pc) ? av : (pb <= pc ? bv : cv)));
+            }
+            return true;
+        default: return false;
+    }
+}
+
+// `rows` scanlines, each = filter byte + rowbytes of data
+__attribute__((noinline)) bool unfilter(uint8_t *data, int rows, size_t rowbytes, int bpp)
+{
+    const uint8_t *prev = nullptr;
+    for (int y = 0; y < rows; y++) {
+        uint8_t *line = data + (rowbytes + 1) * (size_t)y;
+        const int f = *line++;
+        bool ok;
+        switch (bpp) {
+            case 1: ok = unfilter_line<1>(f, line, prev, rowbytes); break;
+            case 2: ok = unfilter_line<2>(f, line, prev, rowbytes); break;
+            case 3: ok = unfilter_line<3>(f, line, prev, rowbytes); break;
+            case 4: ok = unfilter_line<4>(f, line, prev, rowbytes); break;
+            case 6: ok = unfilter_line<6>(f, line, prev, rowbytes); break;
+            case 8: ok = unfilter_line<8>(f, line, prev, rowbytes); break;
+            default: return false;
+        }
+        if (!ok) return false;
+        prev = line;
+    }
+    return true;
+}
+
+struct PngFormat {
+    int depth, ctype, ch;
+    const std::vector<uint8_t> *plte;
+};
+
+// One unfiltered scanline of npix pixels -> gray bytes at dst[j * step], as cv::imread(IMREAD_GRAYSCALE) produces them through libpng:
+// palette -> RGB, gray 1 / 2 / 4 bits scaled to 8, alpha (and tRNS) dropped, RGB -> gray with OpenCV's coefficients
+// ((9797 R + 19234 G + 3737 B) >> 15 at 8 bits; at 16 bits with + 16384 rounding, libpng's 16-bit form), and 16-bit samples
+// reduced to their high byte afterwards (png_set_strip_16).
+__attribute__((noinline)) void to_gray(const PngFormat &F, const uint8_t *row, int npix, uint8_t *dst, size_t step)
+{
+    const int depth = F.depth, ch = F.ch;
+    if (depth == 8) {
+        switch (F.ctype) {
+            case 0: case 4:
+                for (int x = 0; x < npix; x++) dst[x * step] = row[(size_t)x * ch];
+                break;
+            case 3: {
+                const std::vector<uint8_t> &pl = *F.plte;
+                for (int x = 0; x < npix; x++) {
+                    const size_t idx = (size_t)row[x] * 3;
+                    int r = 0, g = 0, bl = 0;
+                    if (idx + 2 < pl.size()) { r = pl[idx]; g = pl[idx + 1]; bl = pl[idx + 2]; }
+                    dst[x * step] = (uint8_t)((9797 * r + 19234 * g + 3737 * bl) >> 15);
+                }
+                break;
+            }
+            default:
+                if (step == 1 && ch == 3) {
+                    for (int x = 0; x < npix; x++) dst[x] = (uint8_t)((9797 * row[3 * x] + 19234 * row[3 * x + 1] + 3737 * row[3 * x + 2]) >> 15);
+                } else if (step == 1) {
+                    for (int x = 0; x < npix; x++) dst[x] = (uint8_t)((9797 * row[4 * x] + 19234 * row[4 * x + 1] + 3737 * row[4 * x + 2]) >> 15);
+                } else {
+                    for (int x = 0; x < npix; x++) {
+                        const uint8_t *q = row + (size_t)x * ch;
+                        dst[x * step] = (uint8_t)((9797 * q[0] + 19234 * q[1] + 3737 * q[2]) >> 15);
+                    }
+                }
+        }
+    } else if (depth == 16) {
+        if (F.ctype == 0 || F.ctype == 4) {
+            for (int x = 0; x < npix; x++) dst[x * step] = row[(size_t)x * ch * 2];
+        } else {
+            for (int x = 0; x < npix; x++) {
+                const uint8_t *q = row + (size_t)x * ch * 2;
+                const uint32_t r = (uint32_t)(q[0] << 8 | q[1]), g = (uint32_t)(q[2] << 8 | q[3]), bl = (uint32_t)(q[4] << 8 | q[5]);
+                dst[x * step] = (uint8_t)(((9797u * r + 19234u * g + 3737u * bl + 16384u) >> 15) >> 8);
+            }
+        }
+    } else { // 1, 2, 4 bits: gray (scaled to 0..255) or palette index, most significant bits first
+        const int per = 8 / depth, mask = (1 << depth) - 1, scale = 255 / mask;
+        const std::vector<uint8_t> *pl = F.ctype == 3 ? F.plte : nullptr;
+        for (int x = 0; x < npix; x++) {
+            const int v = (row[x / per] >> ((per - 1 - x % per) * depth)) & mask;
+            if (!pl) { dst[x * step] = (uint8_t)(v * scale); continue; }
+            const size_t idx = (size_t)v * 3;
+            int r = 0, g = 0, bl = 0;
+            if (idx + 2 < pl->size()) { r = (*pl)[idx]; g = (*pl)[idx + 1]; bl = (*pl)[idx + 2]; }
+            dst[x * step] = (uint8_t)((9797 * r + 19234 * g + 3737 * bl) >> 15);
+        }
+    }
+}
+
+// The reduced images of the stream: the whole image, or Adam7's seven passes (PNG spec 8.2); empty passes carry no data.
+struct Pass { int x0, y0, dx, dy, pw, ph; size_t rowbytes; };
+__attribute__((noinline)) int png_passes(int W, int H, int bits, bool interlace, Pass *passes, size_t *total)
+{
+    static const int kAdam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    int np = 0;
+    *total = 0;
+    if (!interlace) {
+        passes[0] = Pass{0, 0, 1, 1, W, H, ((size_t)W * bits + 7) / 8};
+        *total = (passes[0].rowbytes + 1) * (size_t)H;
+        return 1;
+    }
+    for (int i = 0; i < 7; i++) {
+        const int x0 = kAdam7[i][0], y0 = kAdam7[i][1], dx = kAdam7[i][2], dy = kAdam7[i][3];
+        const int pw = W > x0 ? (W - x0 + dx - 1) / dx : 0, ph = H > y0 ? (H - y0 + dy - 1) / dy : 0;
+        if (pw > 0 && ph > 0) {
+            passes[np] = Pass{x0, y0, dx, dy, pw, ph, ((size_t)pw * bits + 7) / 8};
+            *total += (passes[np].rowbytes + 1) * (size_t)ph;
+            np++;
+        }
+    }
+    return np;
+}
+
+// inflate the concatenated IDAT chunks into `raw`; data past the last scanline is ignored (libpng: a warning), too little fails
+bool inflate_idat(const std::vector<std::pair<const uint8_t *, uint32_t>> &idat, std::vector<uint8_t> &raw)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit(&zs) != Z_OK) return false;
+    zs.next_out = raw.data();
+    zs.avail_out = (uInt)raw.size();
+    int zr = Z_OK;
+    size_t i = 0;
+    while (i < idat.size() && zs.avail_out > 0 && zr == Z_OK) {
+        zs.next_in = const_cast<Bytef *>(idat[i].first);
+        zs.avail_in = idat[i].second;
+        zr = inflate(&zs, Z_NO_FLUSH);
+        i++;
+    }
+    const bool full = zs.avail_out == 0;
+    inflateEnd(&zs);
+    return full && (zr == Z_OK || zr == Z_STREAM_END || zr == Z_BUF_ERROR);
+}
+
 int decode_png(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int *h)
 {
     size_t pos = 8;
     int W = 0, H = 0, depth = 0, ctype = 0, interlace = 0;
-    std::vector<uint8_t> idat, plte;
+    std::vector<uint8_t> plte;
+    std::vector<std::pair<const uint8_t *, uint32_t>> idat;
+    size_t idat_bytes = 0;
     bool have_ihdr = false;
     while (pos + 12 <= n) {
-        uint32_t len = be32(b + pos);
+        const uint32_t len = be32(b + pos);
         const uint8_t *type = b + pos + 4, *data = b + pos + 8;
         if (pos + 12 + (size_t)len > n) return TW_BAD_IMAGE_FORMAT;
-        if (!memcmp(type, "IHDR", 4) && len >= 13) {
+        const bool ihdr = !memcmp(type, "IHDR", 4), is_plte = !memcmp(type, "PLTE", 4), is_idat = !memcmp(type, "IDAT", 4);
+        if (out && (ihdr || is_plte || is_idat) && // libpng fails the read on a critical chunk whose CRC is wrong
+            (uint32_t)crc32(crc32(0L, type, 4), data, len) != be32(data + len)) return TW_BAD_IMAGE_FORMAT;
+        if (ihdr && len >= 13) {
+            if (data[10] != 0 || data[11] != 0) return TW_BAD_IMAGE_FORMAT; // compression / filter method
             W = (int)be32(data); H = (int)be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
             have_ihdr = true;
-        } else if (!memcmp(type, "PLTE", 4)) {
+        } else if (is_plte) {
             plte.assign(data, data + len);
-        } else if (!memcmp(type, "IDAT", 4)) {
-            idat.insert(idat.end(), data, data + len);
+        } else if (is_idat) {
+            idat.emplace_back(data, len);
+            idat_bytes += len;
         } else if (!memcmp(type, "IEND", 4)) {
             break;
         }
         pos += 12 + (size_t)len;
     }
-    if (!have_ihdr || W <= 0 || H <= 0 || depth != 8 || interlace != 0) return TW_BAD_IMAGE_FORMAT;
+    if (!have_ihdr || W <= 0 || H <= 0 || interlace > 1) return TW_BAD_IMAGE_FORMAT;
     int ch;
+    bool ok_depth;
     switch (ctype) {
-        case 0: ch = 1; break;
-        case 2: ch = 3; break;
-        case 3: ch = 1; break;
-        case 4: ch = 2; break;
-        case 6: ch = 4; break;
+        case 0: ch = 1; ok_depth = depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16; break;
+        case 2: ch = 3; ok_depth = depth == 8 || depth == 16; break;
+        case 3: ch = 1; ok_depth = depth == 1 || depth == 2 || depth == 4 || depth == 8; break;
+        case 4: ch = 2; ok_depth = depth == 8 || depth == 16; break;
+        case 6: ch = 4; ok_depth = depth == 8 || depth == 16; break;
         default: return TW_BAD_IMAGE_FORMAT;
     }
-    if (ctype == 3 && plte.size() < 3) return TW_BAD_IMAGE_FORMAT;
+    if (!ok_depth || (ctype == 3 && plte.size() < 3)) return TW_BAD_IMAGE_FORMAT;
     *w = W; *h = H;
     if (!out) return TW_OK;
     if (cap < (size_t)W * H) return TW_BAD_PARAMETER;
-    const size_t stride = (size_t)W * ch;
-    std::vector<uint8_t> raw((stride + 1) * H);
-    uLongf rawlen = (uLongf)raw.size();
-    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return TW_BAD_IMAGE_FORMAT;
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
-    for (int y = 0; y < H; y++) {
-        const uint8_t *line = raw.data() + (stride + 1) * y;
-        const int f = line[0];
-        line++;
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= (size_t)ch ? cur[i - ch] : 0, up = prev[i], c = i >= (size_t)ch ? prev[i - ch] : 0;
-            int v;
-            switch (f) {
-                case 0: v = line[i]; break;
-                case 1: v = line[i] + a; break;
-                case 2: v = line[i] + up; break;
-                case 3: v = line[i] + ((a + up) >> 1); break;
-                case 4: v = line[i] + paeth(a, up, c); break;
-                default: return TW_BAD_IMAGE_FORMAT;
-            }
-            cur[i] = (uint8_t)v;
-        }
-        uint8_t *o = out + (size_t)y * W;
-        for (int x = 0; x < W; x++) {
-            int r, g, bl;
-            if (ctype == 0 || ctype == 4) { o[x] = cur[(size_t)x * ch]; continue; }
-            if (ctype == 3) {
-                size_t idx = (size_t)cur[x] * 3;
-                if (idx + 2 >= plte.size()) { r = g = bl = 0; } else { r = plte[idx]; g = plte[idx + 1]; bl = plte[idx + 2]; }
-            } else {
-                r = cur[(size_t)x * ch]; g = cur[(size_t)x * ch + 1]; bl = cur[(size_t)x * ch + 2];
-            }
-            // libpng rgb_to_gray with OpenCV's coefficients; gray pixels (r == g == b) pass through unchanged
-            o[x] = (r == g && g == bl) ? (uint8_t)r : (uint8_t)((9797 * r + 19234 * g + 3737 * bl) >> 15);
-        }
-        prev.swap(cur);
+    const int bits = ch * depth, bpp = bits >= 8 ? bits / 8 : 1;
+    Pass passes[7];
+    size_t total = 0;
+    const int np = png_passes(W, H, bits, interlace != 0, passes, &total);
+    std::vector<uint8_t> raw(total);
+    if (!inflate_idat(idat, raw)) return TW_BAD_IMAGE_FORMAT;
+    (void)idat_bytes;
+    const PngFormat F{depth, ctype, ch, &plte};
+    uint8_t *data = raw.data();
+    for (int i = 0; i < np; i++) {
+        const Pass &P = passes[i];
+        if (!unfilter(data, P.ph, P.rowbytes, bpp)) return TW_BAD_IMAGE_FORMAT;
+        for (int y = 0; y < P.ph; y++)
+            to_gray(F, data + (P.rowbytes + 1) * (size_t)y + 1, P.pw, out + (size_t)(P.y0 + y * P.dy) * W + P.x0, (size_t)P.dx);
+        data += (P.rowbytes + 1) * P.ph;
     }
     return TW_OK;
 }

@@ -9,6 +9,8 @@
 // so the output does not depend on GPU count or completion order.
 #include "../../include/tidalwave_b200.h"
 
+#include <cuda_runtime_api.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -30,7 +32,7 @@ struct Request { // Request, src/message_queue.h:13-18 (decoded images; `own` ho
     long long id;
     const uint8_t *expect, *target;
     int ew, eh, tw, th;
-    std::shared_ptr<std::vector<uint8_t>> own_e, own_t;
+    std::shared_ptr<uint8_t> own_e, own_t; // pinned buffers of the pool's image store, returned to it when the request is done
 };
 
 struct FileJob { // Request as the reference has it: two paths (src/message_queue.h:13-18)
@@ -66,6 +68,15 @@ struct tw_pool {
     int request_count = 0, data_count = 0, error_count = 0; // Report, src/message_queue.h:44-48
     std::atomic<int> ready{0};
     std::string init_error;
+    // image store of the path-based requests: page-locked host buffers (tw_host_alloc) recycled between requests, so a decoded
+    // image is written once, straight into memory the copy engine reads -- no 2 MB allocation + page faults per image, no
+    // staging of a pageable buffer inside cudaMemcpyAsync on the consumer's thread
+    struct ImageStore {
+        std::mutex mu;
+        std::vector<std::pair<uint8_t *, size_t>> free; // (buffer, capacity)
+        ~ImageStore() { for (auto &b : free) tw_host_free(b.first); }
+    };
+    std::shared_ptr<ImageStore> images = std::make_shared<ImageStore>();
 };
 
 namespace {
@@ -101,17 +112,48 @@ bool read_file(const std::string &path, std::vector<uint8_t> &out)
     return !out.empty();
 }
 
-bool imread_gray(const std::string &path, std::vector<uint8_t> &raw, std::shared_ptr<std::vector<uint8_t>> &img, int &w, int &h)
+std::shared_ptr<uint8_t> take_image(const std::shared_ptr<tw_pool::ImageStore> &st, size_t bytes)
+{
+    uint8_t *buf = nullptr;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lk(st->mu);
+        for (size_t i = 0; i < st->free.size(); i++)
+            if (st->free[i].second >= bytes && st->free[i].second <= 2 * bytes + 4096) { // no 8 MB buffer behind a thumbnail
+                buf = st->free[i].first; cap = st->free[i].second;
+                st->free[i] = st->free.back();
+                st->free.pop_back();
+                break;
+            }
+    }
+    if (!buf) {
+        cap = (bytes + 4095) & ~(size_t)4095;
+        buf = (uint8_t *)tw_host_alloc(cap);
+        if (!buf) { // no page-locked memory to be had: an ordinary buffer, not recycled
+            buf = (uint8_t *)malloc(cap);
+            return std::shared_ptr<uint8_t>(buf, [](uint8_t *b) { free(b); });
+        }
+    }
+    // the deleter keeps the store alive: a request can outlive tw_pool_destroy only inside this translation unit, but the order of
+    // member destruction must not matter
+    return std::shared_ptr<uint8_t>(buf, [st, cap](uint8_t *b) {
+        std::lock_guard<std::mutex> lk(st->mu);
+        if (st->free.size() < 256) st->free.emplace_back(b, cap); else tw_host_free(b);
+    });
+}
+
+bool imread_gray(tw_pool *p, const std::string &path, std::vector<uint8_t> &raw, std::shared_ptr<uint8_t> &img, int &w, int &h)
 {
     if (!read_file(path, raw)) return false;
     if (tw_decode_gray(raw.data(), raw.size(), nullptr, 0, &w, &h) != TW_OK || w < 1 || h < 1) return false;
-    img = std::make_shared<std::vector<uint8_t>>((size_t)w * h);
-    return tw_decode_gray(raw.data(), raw.size(), img->data(), img->size(), &w, &h) == TW_OK;
+    img = take_image(p->images, (size_t)w * h);
+    return img && tw_decode_gray(raw.data(), raw.size(), img.get(), (size_t)w * h, &w, &h) == TW_OK;
 }
 
 void decoder_main(tw_pool *p)
 {
     std::vector<uint8_t> raw;
+    if (!p->devices.empty()) cudaSetDevice(p->devices[0]); // page-locked allocations come from a context the pool uses anyway
     for (;;) {
         FileJob job;
         {
@@ -129,8 +171,8 @@ void decoder_main(tw_pool *p)
         // src/opticalflow.cpp:20-49: empty paths are BadParameter, unreadable / undecodable files BadImageFormat "Can't open <path>"
         if (job.expect.empty()) { fill_error(&e, TW_BAD_PARAMETER, "ExpectImagePath is empty."); ok = false; }
         else if (job.target.empty()) { fill_error(&e, TW_BAD_PARAMETER, "TargetImagePath is empty."); ok = false; }
-        else if (!imread_gray(job.expect, raw, r.own_e, r.ew, r.eh)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.expect).c_str()); ok = false; }
-        else if (!imread_gray(job.target, raw, r.own_t, r.tw, r.th)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.target).c_str()); ok = false; }
+        else if (!imread_gray(p, job.expect, raw, r.own_e, r.ew, r.eh)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.expect).c_str()); ok = false; }
+        else if (!imread_gray(p, job.target, raw, r.own_t, r.tw, r.th)) { fill_error(&e, TW_BAD_IMAGE_FORMAT, ("Can't open " + job.target).c_str()); ok = false; }
         if (!ok) {
             publish(p, job.id, e, nullptr, 0);
             std::lock_guard<std::mutex> lk(p->mu);
@@ -138,7 +180,7 @@ void decoder_main(tw_pool *p)
             p->cv_res.notify_all();
             continue;
         }
-        r.expect = r.own_e->data(); r.target = r.own_t->data();
+        r.expect = r.own_e.get(); r.target = r.own_t.get();
         {
             std::lock_guard<std::mutex> lk(p->mu);
             p->decoding--;
