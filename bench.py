@@ -244,8 +244,9 @@ def run_pool(tw, lib, devices, B, cp, pinned, n_req, warm):
     return dt, nv
 
 
-def run_files_leg(tw, lib, device, B, cp, pairs, n_req=384):
-    """n_req pairs cycled from 16 distinct JPEG pairs on disk through tw_pool_submit_files; -> dict or None (no cv2 to write them)."""
+def run_files_leg(tw, lib, device, B, cp, pairs, n_req=1536, n_png=768):
+    """n_req pairs cycled from 16 distinct JPEG pairs on disk through tw_pool_submit_files (+ n_png pairs from the same images as
+    PNG files); -> dict or None (no cv2 to write them)."""
     import shutil
     import tempfile
     try:
@@ -254,11 +255,12 @@ def run_files_leg(tw, lib, device, B, cp, pairs, n_req=384):
         return None
     d = tempfile.mkdtemp(prefix="tw_bench_files_")
     try:
-        paths = []
+        paths = {"jpg": [], "png": []}
         for i, (a, b) in enumerate(pairs[:16]):
-            pa, pb = os.path.join(d, f"e{i}.jpg"), os.path.join(d, f"t{i}.jpg")
-            cv2.imwrite(pa, a, [cv2.IMWRITE_JPEG_QUALITY, 90]); cv2.imwrite(pb, b, [cv2.IMWRITE_JPEG_QUALITY, 90])
-            paths.append((pa.encode(), pb.encode()))
+            for ext, opt in (("jpg", [cv2.IMWRITE_JPEG_QUALITY, 90]), ("png", [])):
+                pa, pb = os.path.join(d, f"e{i}.{ext}"), os.path.join(d, f"t{i}.{ext}")
+                cv2.imwrite(pa, a, opt); cv2.imwrite(pb, b, opt)
+                paths[ext].append((pa.encode(), pb.encode()))
         perr = C.create_string_buffer(256)
         dv = (C.c_int * 1)(device)
         pool = lib.tw_pool_create(dv, 1, W, H, B, C.byref(cp), 5.0, 10, 4096, perr, 256)
@@ -269,22 +271,30 @@ def run_files_leg(tw, lib, device, B, cp, pairs, n_req=384):
         rvec = (tw.tw_vector * 4096)()
         rres = tw.tw_result()
 
-        def go(n):
-            ids = [lib.tw_pool_submit_files(pool, *paths[i % len(paths)]) for i in range(n)]
+        def go(n, ext):
+            pp = paths[ext]
+            ids = [lib.tw_pool_submit_files(pool, *pp[i % len(pp)]) for i in range(n)]
             for i in ids:
                 if lib.tw_pool_wait(pool, i, rvec, 4096, C.byref(rres)) != 0:
                     raise RuntimeError("file leg: " + rres.reason.decode())
         try:
-            go(2 * B)
+            go(4 * B, "jpg")
             t0 = time.perf_counter()
-            go(n_req)
+            go(n_req, "jpg")
             dt = time.perf_counter() - t0
+            go(B, "png")
+            t0 = time.perf_counter()
+            go(n_png, "png")
+            dt_png = time.perf_counter() - t0
         finally:
             lib.tw_pool_destroy(pool)
         return {"value": n_req / dt, "unit": UNIT, "pairs": n_req, "seconds": dt, "decoder_threads": threads,
                 "api": "tw_pool_submit_files: %d pairs cycled from 16 distinct 1920x1080 JPEG pairs (cv2-written, quality 90) on disk; read + "
-                       "decoded by tw_decode_gray on %d host threads (bit-identical to cv2.imread), then one consumer on the GPU; bound by "
-                       "the host decode" % (n_req, threads)}
+                       "decoded by tw_decode_gray on %d host threads (bit-identical to cv2.imread) into recycled page-locked buffers, then one "
+                       "consumer on the GPU; bound by the host decode" % (n_req, threads),
+                "png": {"value": n_png / dt_png, "unit": UNIT, "pairs": n_png, "seconds": dt_png,
+                        "note": "the same images as 8-bit gray PNG files (cv2-written, default compression): zlib-inflate-bound; half of "
+                                "the pool is band-limited noise texture, which PNG barely compresses"}}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

@@ -2040,6 +2040,113 @@ __global__ void __launch_bounds__(SP_THREADS) gauss_last_sparse_kernel(IterArgs 
     }
 }
 
+// K5s for the default geometry (window radius 15, span 10): one CTA = THREE consecutive sampled rows.  Their 31-row windows
+// overlap by 21 rows, so a thread reads the 51 rows y0 - 15 .. y0 + 35 of its column ONCE into registers (one channel pair at
+// a time) and forms the three vertical sums from them -- 17 rows per output instead of 31 through L2 / L1, the quantity the
+// one-row kernel is bound by.  Tap order per output unchanged, so the results are the same bits.
+constexpr int SP3_R = 3, SP3_M = 15, SP3_SPAN = 10, SP3_ROWS = 2 * SP3_M + 1 + SP3_SPAN * (SP3_R - 1);
+
+template <int FMA> __device__ __forceinline__ float sp3_taps(const float (&win)[SP3_ROWS], const int c, const WinTaps &t)
+{
+    float v = __fmul_rn(win[c], t.k[0]);
+#pragma unroll
+    for (int i = 1; i <= SP3_M; i++) {
+        const float k = t.k[i], dn = win[c + i], up = win[c - i];
+        if (FMA == 2) { v = fmaf(up, k, v); v = fmaf(dn, k, v); }
+        else if (FMA == 1) v = fmaf(__fadd_rn(dn, up), k, v);
+        else v = __fadd_rn(v, __fmul_rn(__fadd_rn(dn, up), k));
+    }
+    return v;
+}
+
+template <int FMA> __global__ void __launch_bounds__(SP_THREADS, 2) gauss_last_sparse3_kernel(IterArgs a, WinTaps t)
+{
+    __shared__ float sv[SP3_R][5][SP_THREADS];
+    __shared__ float sb[SP3_R][SP_MAXS][5];
+    constexpr int m = SP3_M, tw_cols = SP_THREADS - 2 * m;
+    const int tid = threadIdx.x, b = blockIdx.z;
+    const int x0 = blockIdx.x * tw_cols, y0 = blockIdx.y * (SP3_R * SP3_SPAN);
+    const int w = a.d.w, h = a.d.h, pitch = a.d.pitch;
+    const float *Min = a.Min + (size_t)b * 5 * a.d.plane;
+    {
+        const int gx = clampi(x0 - m + tid, 0, w - 1);
+        const size_t rs = (size_t)5 * pitch;
+        const bool interior = y0 - m >= 0 && y0 - m + SP3_ROWS <= h; // CTA-uniform: no row of the window is replicated
+        float wx[SP3_ROWS], wy[SP3_ROWS];
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++) { // channel pairs (0, 1) and (2, 3): 8-byte loads
+            const float *col = Min + (size_t)(2 * pr) * pitch + 2 * gx;
+            if (interior) {
+                const float *p = col + (size_t)(y0 - m) * rs;
+#pragma unroll
+                for (int r = 0; r < SP3_ROWS; r++) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(p + r * rs));
+                    wx[r] = v.x; wy[r] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < SP3_ROWS; r++) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(col + (size_t)clampi(y0 - m + r, 0, h - 1) * rs));
+                    wx[r] = v.x; wy[r] = v.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SP3_R; j++) {
+                sv[j][2 * pr][tid] = sp3_taps<FMA>(wx, m + SP3_SPAN * j, t);
+                sv[j][2 * pr + 1][tid] = sp3_taps<FMA>(wy, m + SP3_SPAN * j, t);
+            }
+        }
+        {
+            const float *col = Min + (size_t)4 * pitch + gx;
+            if (interior) {
+                const float *p = col + (size_t)(y0 - m) * rs;
+#pragma unroll
+                for (int r = 0; r < SP3_ROWS; r++) wx[r] = __ldg(p + r * rs);
+            } else {
+#pragma unroll
+                for (int r = 0; r < SP3_ROWS; r++) wx[r] = __ldg(col + (size_t)clampi(y0 - m + r, 0, h - 1) * rs);
+            }
+#pragma unroll
+            for (int j = 0; j < SP3_R; j++) sv[j][4][tid] = sp3_taps<FMA>(wx, m + SP3_SPAN * j, t);
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass at the sampled columns, for each of the (up to) three rows that exist ----
+    const int s0 = (x0 + SP3_SPAN - 1) / SP3_SPAN;
+    const int ns = max(0, (min(x0 + tw_cols, w) - 1) / SP3_SPAN - s0 + 1);
+    const int nr = min(SP3_R, (h - 1 - y0) / SP3_SPAN + 1); // sampled rows y0 + 10 j < h
+    for (int idx = tid; idx < nr * ns * 5; idx += SP_THREADS) {
+        const int j = idx / (ns * 5), rem = idx - j * (ns * 5), s = rem / 5, c = rem - s * 5;
+        const float *p = &sv[j][c][(s0 + s) * SP3_SPAN - x0 + m];
+        float r = __fmul_rn(p[0], t.k[0]);
+#pragma unroll
+        for (int i = 1; i <= m; i++) {
+            const float k = t.k[i];
+            if (FMA == 2) { r = fmaf(k, p[-i], r); r = fmaf(k, p[i], r); }
+            else if (FMA == 1) r = fmaf(k, __fadd_rn(p[-i], p[i]), r);
+            else r = __fadd_rn(r, __fmul_rn(k, __fadd_rn(p[-i], p[i])));
+        }
+        sb[j][s][c] = r;
+    }
+    __syncthreads();
+    int hit = 0;
+    if (tid < nr * ns) {
+        const int j = tid / ns, s = tid - j * ns;
+        float fx, fy;
+        solve2x2(sb[j][s][0], sb[j][s][1], sb[j][s][2], sb[j][s][3], sb[j][s][4], fx, fy);
+        const int x = (s0 + s) * SP3_SPAN, y = y0 + SP3_SPAN * j;
+        float *f = a.flow + (size_t)b * 2 * a.d.plane + (size_t)y * pitch + x;
+        f[0] = fx; f[a.d.plane] = fy;
+        const float len = __fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy));
+        hit = ((double)len > a.thr2) ? 1 : 0;
+    }
+    if (tid < 96) { // nr * ns <= 3 * 23: three warps cover every sample
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) hit += __shfl_xor_sync(0xffffffffu, hit, off);
+        if ((tid & 31) == 0 && hit > 0) atomicAdd(a.counts + b, hit);
+    }
+}
+
 // Applicable when the samples of a CTA fit its table and the window fits the CTA: else the caller runs the dense kernel.
 bool gauss_last_sparse_ok(const IterArgs &a, const WinTaps &t)
 {
@@ -2052,7 +2159,16 @@ cudaError_t launch_gauss_last_sparse(cudaStream_t s, const IterArgs &a, const Wi
 {
     if (!gauss_last_sparse_ok(a, t)) return cudaErrorInvalidValue;
     const int cols = SP_THREADS - 2 * t.m;
-    dim3 grid((a.d.w + cols - 1) / cols, (a.d.h + a.span - 1) / a.span, a.batch);
+    const int rows = (a.d.h + a.span - 1) / a.span;
+    static const bool one_row = getenv("TW_SPARSE_ROWS") && atoi(getenv("TW_SPARSE_ROWS")) == 1; // measurement switch
+    if (t.m == SP3_M && a.span == SP3_SPAN && !one_row) {
+        dim3 grid((a.d.w + cols - 1) / cols, (rows + SP3_R - 1) / SP3_R, a.batch);
+        if (a.fma == 2) gauss_last_sparse3_kernel<2><<<grid, SP_THREADS, 0, s>>>(a, t);
+        else if (a.fma == 1) gauss_last_sparse3_kernel<1><<<grid, SP_THREADS, 0, s>>>(a, t);
+        else gauss_last_sparse3_kernel<0><<<grid, SP_THREADS, 0, s>>>(a, t);
+        return cudaGetLastError();
+    }
+    dim3 grid((a.d.w + cols - 1) / cols, rows, a.batch);
     gauss_last_sparse_kernel<<<grid, SP_THREADS, 0, s>>>(a, t);
     return cudaGetLastError();
 }
