@@ -467,9 +467,10 @@ def main():
         if world == 1:
             configs = {}
             for key, (w_, h_, b_, kw, gen) in {
-                    "cfg3": (3840, 2160, 4, dict(pyrLevels=5, pyrIterations=5), [("T", 4), ("S", 5), ("T", 14), ("S", 15)]),
-                    "cfg4": (1280, 2000, 8, dict(polyN=5, polySigma=1.1, winSize=15, flags=0), [("S", 3), ("T", 6)] * 4)}.items():
-                prs = [tw.synth.make_pair(k, w_, h_, s, False) for k, s in gen][:b_]
+                    "cfg3": (3840, 2160, 8, dict(pyrLevels=5, pyrIterations=5), [("T", 4), ("S", 5), ("T", 14), ("S", 15)]),
+                    "cfg4": (1280, 2000, 32, dict(polyN=5, polySigma=1.1, winSize=15, flags=0), [("S", 3), ("T", 6)])}.items():
+                made = {ks: tw.synth.make_pair(ks[0], w_, h_, ks[1], False) for ks in dict.fromkeys(gen)}
+                prs = [made[ks] for ks in (gen * b_)[:b_]]  # the batch cycles through the distinct pairs
                 p_ = tw.OpticalFlowParameter(**kw)
                 Rc = Resident(tw, lib, local_rank, prs, p_, w_, h_)
                 ns = 20

@@ -8,12 +8,13 @@ import bench
 import tidalwave_b200 as tw
 key = sys.argv[1]
 cfg = {"cfg2": (1920, 1080, 16, dict(), [("S", 3), ("T", 6)] * 8),
-       "cfg3": (3840, 2160, 4, dict(pyrLevels=5, pyrIterations=5), [("T", 4), ("S", 5), ("T", 14), ("S", 15)]),
-       "cfg4": (1280, 2000, 8, dict(polyN=5, polySigma=1.1, winSize=15, flags=0), [("S", 3), ("T", 6)] * 4)}[key]
+       "cfg3": (3840, 2160, 8, dict(pyrLevels=5, pyrIterations=5), [("T", 4), ("S", 5), ("T", 14), ("S", 15)]),
+       "cfg4": (1280, 2000, 32, dict(polyN=5, polySigma=1.1, winSize=15, flags=0), [("S", 3), ("T", 6)])}[key]
 w, h, b, kw, gen = cfg
 args = [a for a in sys.argv[2:] if "=" not in a]
 if args: b = int(args[0])
-prs = [tw.synth.make_pair(k, w, h, s, False) for k, s in (gen * 8)[:b]]
+made = {ks: tw.synth.make_pair(ks[0], w, h, ks[1], False) for ks in dict.fromkeys(gen)}
+prs = [made[ks] for ks in (gen * b)[:b]]
 lib = tw.load(); dist = tw.dist.Dist(); p = tw.OpticalFlowParameter(**kw)
 R = bench.Resident(tw, lib, 0, prs, p, w, h)
 for a in sys.argv[2:]:
