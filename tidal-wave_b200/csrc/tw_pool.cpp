@@ -158,7 +158,10 @@ void decoder_main(tw_pool *p)
         FileJob job;
         {
             std::unique_lock<std::mutex> lk(p->mu);
-            p->cv_file.wait(lk, [&] { return !p->files.empty() || !p->running; });
+            // back-pressure: decoders stay at most a few batches ahead of the consumers, so the decoded images waiting in page-locked
+            // memory are bounded however many paths have been submitted
+            const size_t ahead = std::max<size_t>(64, (size_t)4 * p->batch * std::max<size_t>(1, p->devices.size()));
+            p->cv_file.wait(lk, [&] { return (!p->files.empty() && p->queue.size() + (size_t)p->decoding < ahead) || !p->running; });
             if (!p->running) return;
             job = std::move(p->files.front());
             p->files.pop_front();
@@ -254,6 +257,7 @@ void consumer_main(tw_pool *p, int idx)
                     work.push_back(q);
                     p->queue.pop_front();
                 }
+                if (!p->files.empty()) p->cv_file.notify_all(); // room for the decoders again
             }
         }
         if (work.empty()) { // nothing new: deliver the oldest batch in flight
