@@ -339,3 +339,17 @@ def test_decode_png_rejects_damaged_streams(tw):
     assert rc(rebuild(raw[:-5])) != 0                 # not enough image data
     assert rc(rebuild(raw + b"\x00" * 40)) == 0       # too much: ignored
     assert rc(rebuild(b"\x07" + raw[1:])) != 0        # filter type 7 does not exist
+
+
+def test_inflate_matches_zlib(tmp_path):
+    """tw_inflate.h (the PNG leg's own zlib-stream decoder) against zlib under ASan + UBSan: tests/cpp/inflate_diff.cpp."""
+    import shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "inflate_diff")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17",
+                           os.path.join(root, "tests", "cpp", "inflate_diff.cpp"), "-lz", "-o", exe])
+    out = subprocess.run([exe, "5", "500"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
+    assert "cases 500 bad 0" in out.stdout

@@ -3,7 +3,8 @@
 //
 //   PNG  every colour type (gray, RGB, palette, gray+alpha, RGBA) at every bit depth the format allows (1 / 2 / 4 / 8 / 16),
 //        Adam7-interlaced or not; critical-chunk CRCs are checked.
-//        zlib inflate + the five PNG row filters; alpha / tRNS is dropped; gray below 8 bits is scaled to 0..255; 16-bit samples
+//        inflate (tw_inflate.h: whole-buffer decoder with a 64-bit bit buffer and two-level tables; zlib decides whatever it
+//        declines) + the five PNG row filters; alpha / tRNS is dropped; gray below 8 bits is scaled to 0..255; 16-bit samples
 //        keep their high byte (16-bit RGB is weighted at 16 bits first, with rounding); colour -> gray exactly as OpenCV's decoder does
 //        it through libpng (png_set_rgb_to_gray with 0.299 / 0.587): gray = (9797*R + 19234*G + 3737*B) >> 15,
 //        truncating (libpng turns 0.299 / 0.587 into the integers 29900*32768/100000 and 58700*32768/100000).  Verified bit-identical to cv2.imread(..., IMREAD_GRAYSCALE) on the reference's PNG fixtures.
@@ -12,6 +13,7 @@
 //        bit-identical to cv2.imread(..., IMREAD_GRAYSCALE) on the reference's progressive scenario1 fixtures).
 //   Anything else: TW_BAD_IMAGE_FORMAT, which the callers report as "Can't open <path>" like a failed imread.
 #include "../../include/tidalwave_b200.h"
+#include "tw_inflate.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -205,9 +207,23 @@ __attribute__((noinline)) int png_passes(int W, int H, int bits, bool interlace,
     return np;
 }
 
-// inflate the concatenated IDAT chunks into `raw`; data past the last scanline is ignored (libpng: a warning), too little fails
+// inflate the concatenated IDAT chunks into `raw`; data past the last scanline is ignored (libpng: a warning), too little fails.
+// tw_inflate.h does the work; whatever it declines goes through zlib, which has the last word.
 bool inflate_idat(const std::vector<std::pair<const uint8_t *, uint32_t>> &idat, std::vector<uint8_t> &raw)
 {
+    static const bool use_fast = !getenv("TW_PNG_ZLIB"); // measurement / bisecting switch
+    if (use_fast && !idat.empty()) {
+        if (idat.size() == 1) {
+            if (tw_inflate::inflate_exact(idat[0].first, idat[0].second, raw.data(), raw.size())) return true;
+        } else {
+            size_t total = 0;
+            for (auto &c : idat) total += c.second;
+            std::vector<uint8_t> joined(total);
+            size_t o = 0;
+            for (auto &c : idat) { memcpy(joined.data() + o, c.first, c.second); o += c.second; }
+            if (tw_inflate::inflate_exact(joined.data(), total, raw.data(), raw.size())) return true;
+        }
+    }
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit(&zs) != Z_OK) return false;
