@@ -330,7 +330,7 @@ TW_AVX2 bool idct_islow_avx2(const int16_t *in, const uint16_t *q, uint8_t *out,
     }
     return true;
 }
-const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+const bool kHaveAvx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2")); // explicit init: this runs as a static constructor
 inline bool idct_islow_lanes(const int16_t *in, const uint16_t *q, uint8_t *out, int stride)
 {
     return kHaveAvx2 && idct_islow_avx2(in, q, out, stride);
