@@ -19,6 +19,9 @@
 #include <cstring>
 #include <vector>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -120,6 +123,33 @@ __attribute__((noinline)) bool unfilter(uint8_t *data, int rows, size_t rowbytes
     return true;
 }
 
+// (9797 R + 19234 G + 3737 B) >> 15 for four pixels at a time: one shuffle spreads (R, G) into 16-bit pairs for a multiply-add
+// against (9797, 19234), another B against 3737 -- exact integers (< 2^23), so the bytes are those of the scalar form.  Returns the
+// number of pixels done (the caller finishes the row; 16-byte loads stay inside it).
+#if defined(__x86_64__)
+__attribute__((target("ssse3"))) int rgb_to_gray_ssse3(const uint8_t *row, int npix, uint8_t *dst, int ch)
+{
+    const __m128i rg3 = _mm_setr_epi8(0, -1, 1, -1, 3, -1, 4, -1, 6, -1, 7, -1, 9, -1, 10, -1), b3 = _mm_setr_epi8(2, -1, -1, -1, 5, -1, -1, -1, 8, -1, -1, -1, 11, -1, -1, -1);
+    const __m128i rg4 = _mm_setr_epi8(0, -1, 1, -1, 4, -1, 5, -1, 8, -1, 9, -1, 12, -1, 13, -1), b4 = _mm_setr_epi8(2, -1, -1, -1, 6, -1, -1, -1, 10, -1, -1, -1, 14, -1, -1, -1);
+    const __m128i mrg = ch == 3 ? rg3 : rg4, mb = ch == 3 ? b3 : b4;
+    const __m128i krg = _mm_setr_epi16(9797, 19234, 9797, 19234, 9797, 19234, 9797, 19234), kb = _mm_setr_epi16(3737, 0, 3737, 0, 3737, 0, 3737, 0);
+    int x = 0;
+    for (; (size_t)(x + 4) * ch + (ch == 3 ? 4 : 0) <= (size_t)npix * ch; x += 4) { // a 16-byte load of 12 needs 4 more bytes in the row
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(row + (size_t)x * ch));
+        const __m128i s = _mm_add_epi32(_mm_madd_epi16(_mm_shuffle_epi8(v, mrg), krg), _mm_madd_epi16(_mm_shuffle_epi8(v, mb), kb));
+        const __m128i g = _mm_srli_epi32(s, 15);
+        const __m128i p = _mm_packus_epi16(_mm_packs_epi32(g, g), g);
+        const int out4 = _mm_cvtsi128_si32(p);
+        memcpy(dst + x, &out4, 4);
+    }
+    return x;
+}
+const bool kHaveSsse3 = (__builtin_cpu_init(), __builtin_cpu_supports("ssse3"));
+inline int rgb_to_gray_simd(const uint8_t *row, int npix, uint8_t *dst, int ch) { return kHaveSsse3 ? rgb_to_gray_ssse3(row, npix, dst, ch) : 0; }
+#else
+inline int rgb_to_gray_simd(const uint8_t *, int, uint8_t *, int) { return 0; }
+#endif
+
 struct PngFormat {
     int depth, ctype, ch;
     const std::vector<uint8_t> *plte;
@@ -149,9 +179,11 @@ __attribute__((noinline)) void to_gray(const PngFormat &F, const uint8_t *row, i
             }
             default:
                 if (step == 1 && ch == 3) {
-                    for (int x = 0; x < npix; x++) dst[x] = (uint8_t)((9797 * row[3 * x] + 19234 * row[3 * x + 1] + 3737 * row[3 * x + 2]) >> 15);
+                    int x = rgb_to_gray_simd(row, npix, dst, 3);
+                    for (; x < npix; x++) dst[x] = (uint8_t)((9797 * row[3 * x] + 19234 * row[3 * x + 1] + 3737 * row[3 * x + 2]) >> 15);
                 } else if (step == 1) {
-                    for (int x = 0; x < npix; x++) dst[x] = (uint8_t)((9797 * row[4 * x] + 19234 * row[4 * x + 1] + 3737 * row[4 * x + 2]) >> 15);
+                    int x = rgb_to_gray_simd(row, npix, dst, 4);
+                    for (; x < npix; x++) dst[x] = (uint8_t)((9797 * row[4 * x] + 19234 * row[4 * x + 1] + 3737 * row[4 * x + 2]) >> 15);
                 } else {
                     for (int x = 0; x < npix; x++) {
                         const uint8_t *q = row + (size_t)x * ch;
