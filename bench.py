@@ -255,11 +255,14 @@ def run_files_leg(tw, lib, device, B, cp, pairs, n_req=1536, n_png=768):
         return None
     d = tempfile.mkdtemp(prefix="tw_bench_files_")
     try:
-        paths = {"jpg": [], "png": []}
+        paths = {"jpg": [], "png": [], "rgb.png": []}
         for i, (a, b) in enumerate(pairs[:16]):
-            for ext, opt in (("jpg", [cv2.IMWRITE_JPEG_QUALITY, 90]), ("png", [])):
+            for ext, opt in (("jpg", [cv2.IMWRITE_JPEG_QUALITY, 90]), ("png", []), ("rgb.png", [])):
                 pa, pb = os.path.join(d, f"e{i}.{ext}"), os.path.join(d, f"t{i}.{ext}")
-                cv2.imwrite(pa, a, opt); cv2.imwrite(pb, b, opt)
+                if ext == "rgb.png":  # colour-typed files (what browsers write): 3 bytes per pixel through inflate / filters / rgb -> gray
+                    cv2.imwrite(pa, cv2.merge([a, a, a]), opt); cv2.imwrite(pb, cv2.merge([b, b, b]), opt)
+                else:
+                    cv2.imwrite(pa, a, opt); cv2.imwrite(pb, b, opt)
                 paths[ext].append((pa.encode(), pb.encode()))
         perr = C.create_string_buffer(256)
         dv = (C.c_int * 1)(device)
@@ -286,6 +289,10 @@ def run_files_leg(tw, lib, device, B, cp, pairs, n_req=1536, n_png=768):
             t0 = time.perf_counter()
             go(n_png, "png")
             dt_png = time.perf_counter() - t0
+            go(B, "rgb.png")
+            t0 = time.perf_counter()
+            go(n_png // 2, "rgb.png")
+            dt_rgb = time.perf_counter() - t0
         finally:
             lib.tw_pool_destroy(pool)
         return {"value": n_req / dt, "unit": UNIT, "pairs": n_req, "seconds": dt, "decoder_threads": threads,
@@ -294,7 +301,10 @@ def run_files_leg(tw, lib, device, B, cp, pairs, n_req=1536, n_png=768):
                        "consumer on the GPU; bound by the host decode" % (n_req, threads),
                 "png": {"value": n_png / dt_png, "unit": UNIT, "pairs": n_png, "seconds": dt_png,
                         "note": "the same images as 8-bit gray PNG files (cv2-written, default compression): zlib-inflate-bound; half of "
-                                "the pool is band-limited noise texture, which PNG barely compresses"}}
+                                "the pool is band-limited noise texture, which PNG barely compresses"},
+                "png_rgb": {"value": (n_png // 2) / dt_rgb, "unit": UNIT, "pairs": n_png // 2, "seconds": dt_rgb,
+                            "note": "the same images as 8-bit RGB PNG files (three equal channels): 3 bytes per pixel through inflate, "
+                                    "the row filters and the rgb -> gray conversion"}}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

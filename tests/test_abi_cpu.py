@@ -278,7 +278,7 @@ def test_decode_png_every_type_depth_interlace(tw):
     lib = tw.load()
     rng = np.random.default_rng(23)
     combos = [(0, d) for d in (1, 2, 4, 8, 16)] + [(2, 8), (2, 16)] + [(3, d) for d in (1, 2, 4, 8)] + [(4, 8), (4, 16), (6, 8), (6, 16)]
-    sizes = [(1, 1), (1, 9), (7, 3), (8, 8), (13, 21), (33, 50), (64, 37)]
+    sizes = [(1, 1), (1, 9), (7, 3), (8, 8), (13, 21), (33, 50), (64, 37), (4, 333)]  # the last: rows long enough for the SIMD Sub / gray paths
     nchan = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
     checked = 0
     for ctype, depth in combos:

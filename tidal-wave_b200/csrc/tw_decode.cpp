@@ -55,6 +55,56 @@ int decode_pgm(const uint8_t *b, size_t n, uint8_t *out, size_t cap, int *w, int
 }
 
 // ---- PNG ----
+// Filter type 1 (Sub) is a running sum per byte lane along the row.  Sixteen (B = 1, 4) or twelve (B = 3) bytes at a time: a
+// log-step prefix sum inside the register (byte shifts by whole pixels), plus the carried last pixel of the previous group
+// broadcast to every pixel -- byte additions wrap exactly like the scalar form.  Returns the number of bytes done.
+#if defined(__x86_64__)
+__attribute__((target("ssse3"))) size_t unfilter_sub_ssse3(uint8_t *line, size_t n, int B)
+{
+    size_t i = 0;
+    if (B == 4) {
+        __m128i carry = _mm_setzero_si128();
+        for (; i + 16 <= n; i += 16) {
+            __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(line + i));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 4));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 8));
+            x = _mm_add_epi8(x, carry);
+            _mm_storeu_si128(reinterpret_cast<__m128i *>(line + i), x);
+            carry = _mm_shuffle_epi32(x, 0xFF);
+        }
+    } else if (B == 1) {
+        __m128i carry = _mm_setzero_si128();
+        const __m128i last = _mm_set1_epi8(15);
+        for (; i + 16 <= n; i += 16) {
+            __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(line + i));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 1));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 2));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 4));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 8));
+            x = _mm_add_epi8(x, carry);
+            _mm_storeu_si128(reinterpret_cast<__m128i *>(line + i), x);
+            carry = _mm_shuffle_epi8(x, last);
+        }
+    } else if (B == 3) {
+        __m128i carry = _mm_setzero_si128();
+        const __m128i keep12 = _mm_setr_epi8(-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0);
+        const __m128i bcast = _mm_setr_epi8(9, 10, 11, 9, 10, 11, 9, 10, 11, 9, 10, 11, -1, -1, -1, -1);
+        for (; i + 16 <= n; i += 12) { // four pixels; the 16-byte load reads 4 bytes of the next group, the stores write 12
+            __m128i x = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(line + i)), keep12);
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 3));
+            x = _mm_add_epi8(x, _mm_slli_si128(x, 6));
+            x = _mm_add_epi8(x, carry);
+            _mm_storel_epi64(reinterpret_cast<__m128i *>(line + i), x);
+            const int hi = _mm_cvtsi128_si32(_mm_srli_si128(x, 8));
+            memcpy(line + i + 8, &hi, 4);
+            carry = _mm_shuffle_epi8(x, bcast);
+        }
+    }
+    return i;
+}
+const bool kHaveSsse3Filter = (__builtin_cpu_init(), __builtin_cpu_supports("ssse3"));
+#endif
+
 // Undo the filter of one scanline in place (PNG spec 9.2).  B = bytes per pixel (1 for sub-byte depths); prev = the unfiltered
 // line above, or nullptr for the first line of an image / pass (all zero).  The left neighbour a and the upper-left c of each of
 // the B byte lanes live in registers: going through line[i - B] would put a store-to-load forward on every byte's critical path.
@@ -66,6 +116,12 @@ template <int B> bool unfilter_line(int f, uint8_t *line, const uint8_t *prev, s
     switch (f) {
         case 0: return true;
         case 1:
+#if defined(__x86_64__)
+            if ((B == 1 || B == 3 || B == 4) && kHaveSsse3Filter && n >= 32) {
+                i = unfilter_sub_ssse3(line, n, B); // a multiple of B bytes
+                for (int k = 0; k < B; k++) a[k] = line[i - B + k];
+            }
+#endif
             for (; i + B <= n; i += B)
                 for (int k = 0; k < B; k++) line[i + k] = a[k] = (uint8_t)(line[i + k] + a[k]);
             for (int k = 0; i < n; i++, k++) line[i] = (uint8_t)(line[i] + a[k]);
