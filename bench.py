@@ -383,7 +383,10 @@ def main():
     traffic, traffic_src = None, None
     try:
         import glob
-        for tf in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_traffic.json")), reverse=True):
+        # newest capture first: r2j is the set of the final commit, the others follow in reverse name order
+        tfs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_traffic.json")), reverse=True)
+        tfs.sort(key=lambda f: not os.path.basename(f).startswith("r2j_"))
+        for tf in tfs:
             tj = json.load(open(tf))
             if tj.get("batch") == B and tj.get("arithmetic", "faithful") == arithmetic and top in tj:
                 traffic = tj[top]["dram_bytes_per_launch"]
