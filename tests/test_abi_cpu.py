@@ -285,6 +285,11 @@ def test_decode_png_every_type_depth_interlace(tw):
         for interlace in (0, 1):
             for (h, w) in sizes:
                 samples = rng.integers(0, 1 << depth, (h, w, nchan[ctype]))
+                if w > 100:  # screenshot-like structure: flat runs and repeated rows (the degenerate Paeth groups of the SIMD filter path)
+                    samples[:, w // 4: w // 2] = samples[:, w // 4: w // 4 + 1]
+                    samples[2:] = samples[1]
+                    samples[3, w // 3] += 1
+                    samples %= 1 << depth
                 palette = rng.integers(0, 256, (1 << depth, 3)) if ctype == 3 else None
                 trns = None
                 if rng.integers(0, 2):  # transparency information must not change the gray output

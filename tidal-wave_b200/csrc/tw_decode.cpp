@@ -102,6 +102,78 @@ __attribute__((target("ssse3"))) size_t unfilter_sub_ssse3(uint8_t *line, size_t
     }
     return i;
 }
+// Filter type 4 (Paeth) is a serial chain per byte, but on screenshot content it mostly degenerates, and both degenerate forms can
+// be recognised for a whole group of pixels (16 bytes, 12 for B = 3) before any of its bytes is computed:
+//   (A) the row above is locally flat, b == c at every byte of the group: then p = a, |p - a| = 0 and the predictor is a -- the group
+//       is a running sum, done in the register like filter type 1;
+//   (B) the row above continues into this one: speculate predictor b (out = x + b) and check that every left neighbour then equals
+//       its upper-left, a == c -- there |p - b| = 0 and the predictor is b unless |p - a| = 0 too, where a == b == c anyway.
+// Groups that are neither run the scalar predictor.  Same bytes as the scalar form by construction.
+template <int B> __attribute__((target("ssse3"))) void unfilter_paeth_ssse3(uint8_t *line, const uint8_t *prev, size_t n)
+{
+    const size_t G = B == 3 ? 12 : 16;
+    const __m128i keep = B == 3 ? _mm_setr_epi8(-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0) : _mm_set1_epi8(-1);
+    const int want = B == 3 ? 0x0FFF : 0xFFFF;
+    const __m128i lowB = B == 1 ? _mm_setr_epi8(-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+                       : B == 3 ? _mm_setr_epi8(-1, -1, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+                                : _mm_setr_epi8(-1, -1, -1, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m128i bcast = B == 1 ? _mm_setzero_si128()
+                        : B == 3 ? _mm_setr_epi8(0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2, -1, -1, -1, -1)
+                                 : _mm_setr_epi8(0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3);
+    for (int k = 0; k < B && (size_t)k < n; k++) line[k] = (uint8_t)(line[k] + prev[k]); // first pixel: a = c = 0, the predictor is b
+    size_t i = (size_t)B;
+    __m128i lastpix = _mm_setzero_si128(); // the pixel left of the group in the low B bytes
+    bool have_last = false;
+    while (i + 16 <= n) {
+        if (!have_last) {
+            int w = 0;
+            memcpy(&w, line + i - B, (size_t)B);
+            lastpix = _mm_cvtsi32_si128(w);
+        }
+        const __m128i P = _mm_loadu_si128(reinterpret_cast<const __m128i *>(prev + i));
+        const __m128i Pm = _mm_loadu_si128(reinterpret_cast<const __m128i *>(prev + i - B));
+        const __m128i X = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(line + i)), keep);
+        __m128i out;
+        bool simd = true;
+        if ((_mm_movemask_epi8(_mm_cmpeq_epi8(P, Pm)) & want) == want) { // (A) running sum
+            out = _mm_add_epi8(X, _mm_slli_si128(X, B == 1 ? 1 : B == 3 ? 3 : 4));
+            out = _mm_add_epi8(out, _mm_slli_si128(out, B == 1 ? 2 : B == 3 ? 6 : 8));
+            if (B == 1) { out = _mm_add_epi8(out, _mm_slli_si128(out, 4)); out = _mm_add_epi8(out, _mm_slli_si128(out, 8)); }
+            out = _mm_add_epi8(out, _mm_shuffle_epi8(lastpix, bcast));
+        } else {
+            out = _mm_add_epi8(X, _mm_and_si128(P, keep)); // (B) speculate predictor b
+            const __m128i left = _mm_or_si128(B == 1 ? _mm_slli_si128(out, 1) : B == 3 ? _mm_slli_si128(out, 3) : _mm_slli_si128(out, 4), _mm_and_si128(lastpix, lowB));
+            simd = (_mm_movemask_epi8(_mm_cmpeq_epi8(left, Pm)) & want) == want;
+        }
+        if (simd) {
+            if (B == 3) {
+                _mm_storel_epi64(reinterpret_cast<__m128i *>(line + i), out);
+                const int hi = _mm_cvtsi128_si32(_mm_srli_si128(out, 8));
+                memcpy(line + i + 8, &hi, 4);
+                lastpix = _mm_srli_si128(out, 9);
+            } else {
+                _mm_storeu_si128(reinterpret_cast<__m128i *>(line + i), out);
+                lastpix = B == 1 ? _mm_srli_si128(out, 15) : _mm_srli_si128(out, 12);
+            }
+            have_last = true;
+        } else {
+            for (size_t j = i; j < i + G; j++) {
+                const int av = line[j - B], bv = prev[j], cv = prev[j - B];
+                const int pa0 = bv - cv, pb0 = av - cv;
+                const int pa = abs(pa0), pb = abs(pb0), pc = abs(pa0 + pb0);
+                line[j] = (uint8_t)(line[j] + ((pa <= pb && pa <= pc) ? av : (pb <= pc ? bv : cv)));
+            }
+            have_last = false;
+        }
+        i += G;
+    }
+    for (; i < n; i++) {
+        const int av = line[i - B], bv = prev[i], cv = prev[i - B];
+        const int pa0 = bv - cv, pb0 = av - cv;
+        const int pa = abs(pa0), pb = abs(pb0), pc = abs(pa0 + pb0);
+        line[i] = (uint8_t)(line[i] + ((pa <= pb && pa <= pc) ? av : (pb <= pc ? bv : cv)));
+    }
+}
 const bool kHaveSsse3Filter = (__builtin_cpu_init(), __builtin_cpu_supports("ssse3"));
 #endif
 
@@ -136,6 +208,9 @@ template <int B> bool unfilter_line(int f, uint8_t *line, const uint8_t *prev, s
             return true;
         case 4:
             if (!prev) return unfilter_line<B>(1, line, prev, n); // b = c = 0: the predictor is a
+#if defined(__x86_64__)
+            if ((B == 1 || B == 3 || B == 4) && kHaveSsse3Filter && n >= 32) { unfilter_paeth_ssse3<(B == 1 || B == 3 || B == 4) ? B : 1>(line, prev, n); return true; }
+#endif
             for (; i + B <= n; i += B)
                 for (int k = 0; k < B; k++) {
                     const int av = a[k], bv = prev[i + k], cv = c[k];
