@@ -105,6 +105,16 @@ bool read_file(const std::string &path, std::vector<uint8_t> &out)
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
     out.clear();
+    if (fseek(f, 0, SEEK_END) == 0) { // regular file: one read of its size
+        const long size = ftell(f);
+        if (size > 0 && fseek(f, 0, SEEK_SET) == 0) {
+            out.resize((size_t)size);
+            out.resize(fread(out.data(), 1, (size_t)size, f));
+            fclose(f);
+            return !out.empty();
+        }
+        rewind(f);
+    }
     uint8_t buf[1 << 16];
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + n);
